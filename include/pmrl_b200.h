@@ -1,0 +1,225 @@
+/*
+ * pmrl_b200.h — C-ABI of libpmrl_b200.so: the B200 (sm_100a) implementation of the
+ * pm-rl portfolio-environment hot path, batched over E lockstep environments.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a CUDA
+ * stream handle (as void*), enqueues work on that stream and returns immediately
+ * (no host sync, no allocation, no global state; graph-capturable).  Return value:
+ * 0 = ok, negative = PMRL_E_* (argument/shape problem, nothing was launched),
+ * positive = a cudaError_t from the launch.  `pmrl_last_error()` gives the text.
+ *
+ * Reference interfaces replaced (all paths relative to the pm-rl tree):
+ *   pmrl_env_reset      <- TradingEnv.reset              env/sim/trading_env.py:21-41
+ *                          ActionBuffer.reset            env/sim/weight_buffer.py:46-50
+ *   pmrl_env_step       <- TradingEnv.step               env/sim/trading_env.py:44-105
+ *                          ActionBuffer.update/get_last  env/sim/weight_buffer.py:13-30
+ *                          ActionBuffer.get_all          env/sim/weight_buffer.py:32-44
+ *                          Reward.get_reward & variants  env/reward.py:15-31
+ *                          y_t = close_t/close_{t-1}     data/instrument.py:79
+ *                          window rows [i, i+W)          data/instrument.py:351-356
+ *   pmrl_obs_build      <- features[:, :, -1] = weights.get_all()   trading_env.py:32,103
+ *   pmrl_ffd_weights    <- FixedFracDiff._objective (weights/width) data/ffd.py:38-47
+ *   pmrl_ffd_transform  <- FixedFracDiff.transform       data/ffd.py:80-89
+ *   pmrl_scale_series   <- Instrument.scale              data/instrument.py:318-336
+ *   pmrl_pack_features  <- Instrument.window / get_feature_tensor layout (instrument.py:339-356)
+ *   pmrl_rollout_add    <- RolloutBuffer.add             replay/rollout_buffer.py:43-57
+ *   pmrl_rollout_gather <- RolloutBuffer.sample[_random] replay/rollout_buffer.py:59-142
+ *   pmrl_replay_add     <- ReplayBuffer.add              replay/buffer.py:23-37, replay/traj_buffer.py:26-43
+ *   pmrl_replay_gather  <- ReplayBuffer.sample           replay/buffer.py:39-79, replay/traj_buffer.py:45-89
+ *   pmrl_pg_reward_*    <- PG._reward (fwd + grad wrt a) agent/pg/pg.py:40-82
+ *   pmrl_eval_metrics   <- Metrics.sharpe/sortino/mdd/average_turnover  util/eval.py:14-37
+ *
+ * Device data layout (all fp32 unless noted; E = envs on this GPU, A = assets incl.
+ * cash at index 0, W = window, F = obs channels incl. the weight slot which is LAST):
+ *   close_tm [T, A]        time-major close plane; y_t[a] = close_tm[t,a] / close_tm[t-1,a]
+ *   feat_am  [A, T, F-1]   asset-major feature table (OHLC, or FFD'ed + scaled series)
+ *   value    [E]           portfolio value V
+ *   hist     [E, W, A]     ring of post-drift weights (reference ActionBuffer.buffer per env)
+ *   idx      [E] i32       ring write pointer;  is_full [E] u8;  t [E] i32 local step k
+ *   t0       [E] i32       episode offset: at local step k the env sees table rows
+ *                          [t0+k, t0+k+W) and the price relative of row t0+k+W-1
+ *   obs      [E, A, W, F]  reference observation layout (net/lsre_cann.py:105)
+ */
+#ifndef PMRL_B200_H
+#define PMRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMRL_ABI_VERSION 1
+
+/* error codes (negative) */
+#define PMRL_E_ARG        (-1)   /* null pointer / bad enum */
+#define PMRL_E_SHAPE      (-2)   /* unsupported or inconsistent sizes */
+#define PMRL_E_ALIGN      (-3)   /* pointer alignment requirement not met */
+
+/* reward_mode (env/reward.py:15-18, trading_env.py:93-99) */
+#define PMRL_REWARD_STEP_LOG    0   /* ln(V'/V_post_mu) * scale  — what TradingEnv.step returns (:99) */
+#define PMRL_REWARD_RETURNS     1   /* Reward.returns      (env/reward.py:20-21) */
+#define PMRL_REWARD_LOG_RETURNS 2   /* Reward.log_returns  (env/reward.py:23-24) */
+#define PMRL_REWARD_SHARPE      3   /* Reward.sharpe_ratio (env/reward.py:26-31), running over the episode */
+
+/* cfg.flags */
+#define PMRL_FLAG_STRICT_REFERENCE 1u  /* reproduce quirk Q1: normalise only if (!isclose(sum,1) AND min<0).
+                                          cleared: OR-condition + max-subtracted softmax (agent/pg/pg.py:52-53) */
+
+/* obs_mode of pmrl_env_step / pmrl_env_reset */
+#define PMRL_OBS_NONE    0   /* state-only step ("Mode S") */
+#define PMRL_OBS_FULL    1   /* gather feature window + weight channel into obs ("Mode O") */
+#define PMRL_OBS_WEIGHTS 2   /* overwrite only channel F-1 of a caller-filled obs (compat shim; trading_env.py:103) */
+
+typedef struct PmrlEnvCfg {
+    int32_t E, A, W, F;        /* envs on this device, assets, window, obs channels (weight slot = F-1) */
+    int32_t T;                 /* rows of close_tm / feat_am */
+    int32_t episode_len;       /* L_ep: done when local step == L_ep; <= 0 → episodes never end */
+    int32_t reward_mode;       /* PMRL_REWARD_* */
+    int32_t mu_max_iter;       /* cap on the commission fixed-point iterations (trading_env.py:70) */
+    uint32_t flags;            /* PMRL_FLAG_* */
+    float initial_cash;        /* config/base.py:47 INITIAL_CASH */
+    float commission;          /* config/base.py:48 COMISSION [sic] */
+    float reward_scale;        /* config/base.py:52 REWARD_SCALE */
+    float risk_free;           /* config/base.py:53 RISK_FREE_RATE */
+} PmrlEnvCfg;
+
+typedef struct PmrlTables {
+    const float* close_tm;     /* [T, A] or NULL when y is supplied externally */
+    const float* feat_am;      /* [A, T, F-1] or NULL when obs_mode != PMRL_OBS_FULL */
+} PmrlTables;
+
+typedef struct PmrlEnvState {
+    float*    value;           /* [E] */
+    float*    hist;            /* [E, W, A] */
+    int32_t*  idx;             /* [E] */
+    uint8_t*  is_full;         /* [E] */
+    int32_t*  t;               /* [E] */
+    const int32_t* t0;         /* [E] (may be NULL when y_ext is used and obs_mode != FULL) */
+    double*   sharpe;          /* [E, 3] running (n, mean, M2) of gross returns; required for PMRL_REWARD_SHARPE */
+    float*    ep_return;       /* [E] running sum of rewards in the episode; required when stats != NULL */
+} PmrlEnvState;
+
+/* stats vector written by pmrl_env_step (accumulated with atomics; caller zeroes it) */
+#define PMRL_STATS_LEN 10
+#define PMRL_STAT_N_ENVS     0   /* envs that took a real step */
+#define PMRL_STAT_SUM_R      1
+#define PMRL_STAT_SUM_R2     2
+#define PMRL_STAT_SUM_V      3
+#define PMRL_STAT_SUM_LNV    4
+#define PMRL_STAT_N_DONE     5
+#define PMRL_STAT_SUM_EPRET  6   /* Σ episode return over envs that finished this step */
+#define PMRL_STAT_SUM_EPLEN  7
+#define PMRL_STAT_MAX_V      8   /* max V   (caller initialises to -inf) */
+#define PMRL_STAT_MAX_NEGV   9   /* max −V  (caller initialises to -inf) → min V = −this */
+
+int         pmrl_abi_version(void);
+const char* pmrl_last_error(void);
+
+/* Re-initialise the envs with mask[e] != 0 (mask == NULL → all): V ← initial_cash, ring ← 0 with
+ * hist[e,0,0] = 1, idx ← 1, is_full ← 0, t ← 0, sharpe/ep_return cleared.  If obs_mode != NONE the
+ * obs of the (re)initialised envs is written (window rows [t0, t0+W) + reset weight channel). */
+int pmrl_env_reset(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
+                   const uint8_t* mask, float* obs, int32_t obs_mode, void* stream);
+
+/* One lockstep transition of all E envs.
+ *   actions [E, A]  raw scores or weights (normalised in-kernel like trading_env.py:58-60)
+ *   y_ext   [E, A]  externally supplied price relatives, or NULL → computed from tbl->close_tm
+ *   reward  [E]     out;  done [E] u8 out (local step reached episode_len)
+ *   obs             out [E,A,W,F] (FULL), in/out (WEIGHTS), or NULL (NONE)
+ *   stats           double[PMRL_STATS_LEN] device vector or NULL
+ * An env whose local step already equals episode_len on entry is auto-reset instead of stepped
+ * (reward 0, done 0, action ignored) — the reference loop's `if step == 0: env.reset(data)`
+ * (train/on_policy.py:60-61). */
+int pmrl_env_step(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
+                  const float* actions, const float* y_ext,
+                  float* reward, uint8_t* done, float* obs, int32_t obs_mode,
+                  double* stats, void* stream);
+
+/* Materialise obs for the current state without stepping (obs_mode FULL or WEIGHTS). */
+int pmrl_obs_build(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
+                   float* obs, int32_t obs_mode, void* stream);
+
+/* ---- feature path (data/ffd.py, data/instrument.py) ---- */
+
+/* Binomial FFD weights per series: w[n,0]=1, w[n,k]=w[n,k-1]*(1-(d[n]+1)/k) (sequential fp32 product,
+ * ffd.py:38-40; d is a host-precision double like the reference's Python float, rounded to fp32 after
+ * the +1); widths[n] = max{k : |w[n,k]| > thres} (ffd.py:43).  d [N] f64 (device), weights [N, T], widths [N] i32. */
+int pmrl_ffd_weights(const double* d, int32_t N, int32_t T, float thres,
+                     float* weights, int32_t* widths, void* stream);
+
+/* Valid convolution with the first widths[n] taps (the tap at index width is dropped, ffd.py:47),
+ * tail-aligned to T - max_width outputs (ffd.py:81-88):
+ *   out[n, j] = Σ_{k<width_n} w[n,k] · x[n, max_width + j − k],  j ∈ [0, T−max_width)
+ * Series with d[n] <= 0 are copied (x[n, max_width + j]).  x [N, T], out [N, T − max_width]. */
+int pmrl_ffd_transform(const float* x, const double* d, const float* weights, const int32_t* widths,
+                       int32_t N, int32_t T, int32_t max_width, float* out, void* stream);
+
+/* Per-series scaling over [0, L): method 0 = min-max (x−min)/(max−min), 1 = standard (x−mean)/std (population
+ * std), constant series follow sklearn (scale treated as 1).  In place allowed (out == x).  x [N, L]. */
+int pmrl_scale_series(const float* x, int32_t N, int32_t L, int32_t method, float* out, void* stream);
+
+/* Pack series-major planes into the two table layouts the env kernels read:
+ *   series [A*C, L] (series index = a*C + c)  →  feat_am [A, L, C];  close [A, L] → close_tm [L, A]. */
+int pmrl_pack_features(const float* series, const float* close, int32_t A, int32_t C, int32_t L,
+                       float* feat_am, float* close_tm, void* stream);
+
+/* ---- buffers (replay/rollout_buffer.py, replay/buffer.py, replay/traj_buffer.py) ---- */
+
+/* On-policy store, batched over envs: slot = step − (W−1) when step > W−1 (rollout_buffer.py:51-57).
+ * Buffers: s [S, E, A, W, F], a [S, E, A], v [S, E], r [S, E].  Copies obs/action/value/reward of all E
+ * envs into `slot` (the step kernel can also write obs straight into s[slot] — then pass obs == NULL). */
+int pmrl_rollout_add(int32_t E, int32_t A, int32_t W, int32_t F, int32_t slot,
+                     const float* obs, const float* action, const float* value, const float* reward,
+                     float* s, float* a, float* v, float* r, void* stream);
+
+/* Minibatch gather (rollout_buffer.py:125-140): for b < B with (slot_b, env_b):
+ *   s_out[b] = s[slot,env], a_out[b] = a[slot,env], r_out[b] = r[slot,env],
+ *   pv_out[b] = v[slot−1,env], pa_out[b] = a[slot−1,env], p_out[b] = y[slot,env] (price relatives [S,E,A]). */
+int pmrl_rollout_gather(int32_t S, int32_t E, int32_t A, int32_t W, int32_t F, int32_t B,
+                        const int32_t* slots, const int32_t* envs,
+                        const float* s, const float* a, const float* v, const float* r, const float* y,
+                        float* s_out, float* a_out, float* r_out, float* pv_out, float* pa_out, float* p_out,
+                        void* stream);
+
+/* Off-policy index replay: store (i, a, r) of all E envs at [epoch_slot, step_slot] (buffer.py:31-37).
+ * Buffers: bi [P, L, E] i32, ba [P, L, E, A], br [P, L, E]. */
+int pmrl_replay_add(int32_t P, int32_t L, int32_t E, int32_t A, int32_t epoch_slot, int32_t step_slot,
+                    const int32_t* item_index, const float* action, const float* reward,
+                    int32_t* bi, float* ba, float* br, void* stream);
+
+/* Off-policy sample (buffer.py:58-77): for b < B with (epoch_b, env_b, start_b), end = start+W:
+ *   i = bi[epoch, end−1, env];  s[b] = window rows [i, i+W) of feat_am, s_[b] = rows [i+1, i+1+W);
+ *   channel F−1 of s ← ba[epoch, start:end, env, :]ᵀ, of s_ ← ba[epoch, start+1:end+1, env, :]ᵀ;
+ *   a[b] = ba[epoch, end, env, :];  r[b] = br[epoch, end−1, env]. */
+int pmrl_replay_gather(int32_t P, int32_t L, int32_t E, int32_t A, int32_t W, int32_t F, int32_t T, int32_t B,
+                       const int32_t* epochs, const int32_t* envs, const int32_t* starts,
+                       const int32_t* bi, const float* ba, const float* br, const float* feat_am,
+                       float* s_out, float* a_out, float* r_out, float* s2_out, void* stream);
+
+/* ---- differentiable batched reward (agent/pg/pg.py:40-82) ---- */
+
+/* Forward: per row b: a' = softmax(a) if normalise else a; mu (commission) ; v = Σ pv·(a'·p); ret = v/(mu·pv);
+ * rew[b] = {ret, ln ret}·scale;  Backward: grad_a[b,:] = d(mean_b rew)/d a[b,:]·gscale.
+ * a [B, A], pv [B], pa [B, A] (previous weights), p [B, A].  mode: PMRL_REWARD_RETURNS | _LOG_RETURNS. */
+int pmrl_pg_reward_fwd_bwd(int32_t B, int32_t A, int32_t mode, int32_t normalise, float commission, float scale,
+                           int32_t mu_max_iter,
+                           const float* a, const float* pv, const float* pa, const float* p,
+                           float* rew, float* grad_a, float gscale, void* stream);
+
+/* ---- evaluation metrics on device (util/eval.py:14-37) ---- */
+
+/* values [E, N] per-env portfolio-value history (values[:,0] = initial cash), weights [E, N, A] or NULL.
+ * out [E, 4] = {sharpe, sortino, max drawdown, average turnover} with simple returns r_i = V_i/V_{i-1} - 1,
+ * excess e_i = r_i - ((1+rf)^(1/periods) - 1):
+ *   sharpe  = mean(e)/std(e, ddof=1)*sqrt(periods);  sortino = mean(e)/sqrt(sum(min(e,0)^2)/n)*sqrt(periods)
+ *   (the published quantstats formulas util/eval.py:14-24 calls — quantstats itself is not vendored: UNPINNED);
+ *   mdd     = min_i(V_i / max_{j<=i} V_j) - 1                         (util/eval.py:26-30)
+ *   turnover = mean_{i>=1} sum_a |w[i,a] - w[i-1,a]|                   (util/eval.py:32-37, pinned) */
+int pmrl_eval_metrics(const float* values, const float* weights, int32_t E, int32_t N, int32_t A,
+                      float rf, int32_t periods, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMRL_B200_H */

@@ -1,0 +1,66 @@
+"""Harness that imports the LIVE reference (read-only tree at /root/reference) — test infrastructure.
+
+Only usable where the reference tree exists (the build container); it never travels to the GPU box.
+It is used (a) by tests/golden/make_golden.py to produce the committed fixtures and (b) by
+tests marked `needs_reference` to cross-check the restated oracle against the reference itself.
+
+The reference binds its shape constants by value at import (`from config.base import WINDOW_SIZE,
+NUM_ASSETS`, env/sim/weight_buffer.py:1), so the harness patches `config.base` and reloads the env
+modules for every shape.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+
+REFERENCE_ROOT = os.environ.get("PMRL_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "env", "sim", "trading_env.py"))
+
+
+def _ensure_path():
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    sys.dont_write_bytecode = True            # the tree is read-only
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+
+
+def load_env_module(num_assets: int, window: int, commission: float = 0.0, patch_maximum: bool = False):
+    """Returns the reference's `env.sim.trading_env` module bound to (num_assets, window, commission).
+
+    patch_maximum=True wraps `torch.maximum` *inside that module only* so that the broken one-argument
+    call at trading_env.py:72 evaluates relu(x) (the upstream PGPortfolio form it cites at :66)."""
+    _ensure_path()
+    import config.base as cb
+    cb.NUM_ASSETS, cb.WINDOW_SIZE, cb.COMISSION = int(num_assets), int(window), float(commission)
+    import env.sim.weight_buffer as wb
+    import env.reward as rw
+    import env.sim.trading_env as te
+    importlib.reload(wb)
+    importlib.reload(rw)
+    importlib.reload(te)
+    if patch_maximum:
+        import types
+        import torch
+
+        class _TorchProxy(types.ModuleType):
+            def __getattr__(self, name):
+                return getattr(torch, name)
+
+        proxy = _TorchProxy("torch")
+        proxy.maximum = lambda x, *a: torch.maximum(x, *a) if a else torch.clamp_min(x, 0)
+        te.torch = proxy
+    return te
+
+
+def load_rollout_buffer_module(num_assets: int, window: int, batch_size: int):
+    _ensure_path()
+    import config.base as cb
+    cb.NUM_ASSETS, cb.WINDOW_SIZE, cb.BATCH_SIZE = int(num_assets), int(window), int(batch_size)
+    import replay.rollout_buffer as rb
+    importlib.reload(rb)
+    return rb

@@ -1,0 +1,112 @@
+"""ctypes binding of libpmrl_b200.so — the only way the Python host reaches the CUDA kernels.
+
+There is no CPU fallback: if the library cannot be loaded, or a call is made without a CUDA device,
+the error is raised to the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpmrl_b200.so")
+
+c_float_p = C.c_void_p     # device pointers travel as integers
+c_void_p = C.c_void_p
+i32 = C.c_int32
+f32 = C.c_float
+
+
+class PmrlEnvCfg(C.Structure):
+    _fields_ = [("E", i32), ("A", i32), ("W", i32), ("F", i32), ("T", i32),
+                ("episode_len", i32), ("reward_mode", i32), ("mu_max_iter", i32), ("flags", C.c_uint32),
+                ("initial_cash", f32), ("commission", f32), ("reward_scale", f32), ("risk_free", f32)]
+
+
+class PmrlTables(C.Structure):
+    _fields_ = [("close_tm", c_void_p), ("feat_am", c_void_p)]
+
+
+class PmrlEnvState(C.Structure):
+    _fields_ = [("value", c_void_p), ("hist", c_void_p), ("idx", c_void_p), ("is_full", c_void_p),
+                ("t", c_void_p), ("t0", c_void_p), ("sharpe", c_void_p), ("ep_return", c_void_p)]
+
+
+P = C.POINTER
+# symbol → (restype, argtypes); must list every function declared in include/pmrl_b200.h
+SIGNATURES = {
+    "pmrl_abi_version": (C.c_int, []),
+    "pmrl_last_error": (C.c_char_p, []),
+    "pmrl_env_reset": (C.c_int, [P(PmrlEnvCfg), P(PmrlTables), P(PmrlEnvState), c_void_p, c_void_p, i32, c_void_p]),
+    "pmrl_env_step": (C.c_int, [P(PmrlEnvCfg), P(PmrlTables), P(PmrlEnvState), c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, i32, c_void_p, c_void_p]),
+    "pmrl_obs_build": (C.c_int, [P(PmrlEnvCfg), P(PmrlTables), P(PmrlEnvState), c_void_p, i32, c_void_p]),
+    "pmrl_ffd_weights": (C.c_int, [c_void_p, i32, i32, f32, c_void_p, c_void_p, c_void_p]),
+    "pmrl_ffd_transform": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, i32, i32, i32, c_void_p, c_void_p]),
+    "pmrl_scale_series": (C.c_int, [c_void_p, i32, i32, i32, c_void_p, c_void_p]),
+    "pmrl_pack_features": (C.c_int, [c_void_p, c_void_p, i32, i32, i32, c_void_p, c_void_p, c_void_p]),
+    "pmrl_rollout_add": (C.c_int, [i32, i32, i32, i32, i32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pmrl_rollout_gather": (C.c_int, [i32, i32, i32, i32, i32, i32, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pmrl_replay_add": (C.c_int, [i32, i32, i32, i32, i32, i32, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pmrl_replay_gather": (C.c_int, [i32, i32, i32, i32, i32, i32, i32, i32, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pmrl_pg_reward_fwd_bwd": (C.c_int, [i32, i32, i32, i32, f32, f32, i32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, f32, c_void_p]),
+    "pmrl_eval_metrics": (C.c_int, [c_void_p, c_void_p, i32, i32, i32, f32, i32, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+class PmrlError(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = False) -> C.CDLL:
+    """dlopen libpmrl_b200.so (in-tree).  Raises if it is missing — there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if build_if_missing:
+            from . import build as _b
+            _b.build()
+        else:
+            raise PmrlError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(nvcc, sm_100a). pmrl_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here means header and library diverged
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pmrl_abi_version() != 1:
+        raise PmrlError("libpmrl_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().pmrl_last_error().decode(errors="replace")
+        raise PmrlError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a CUDA tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise PmrlError("pmrl_b200 kernels need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise PmrlError("pmrl_b200 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

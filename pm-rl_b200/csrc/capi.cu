@@ -1,0 +1,35 @@
+// capi.cu — ABI version, error reporting and device-query helpers of libpmrl_b200.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include "pmrl_b200.h"
+#include "host_util.h"
+
+static thread_local char g_err[256] = "";
+
+int pmrl_fail(int code, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "pmrl_b200: %s", msg);
+    return code;
+}
+
+int pmrl_check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return 0;
+    snprintf(g_err, sizeof(g_err), "pmrl_b200: launch of %s failed: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+
+int pmrl_sm_count(void) {
+    static int cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+extern "C" int pmrl_abi_version(void) { return PMRL_ABI_VERSION; }
+extern "C" const char* pmrl_last_error(void) { return g_err; }

@@ -1,0 +1,244 @@
+// env_step.cuh — one warp advances one environment by one step.
+//
+// Restates, batched and in registers, the reference transition
+//   TradingEnv.step            env/sim/trading_env.py:54-100
+//   ActionBuffer.update/get_last  env/sim/weight_buffer.py:13-30
+//   Reward.*                   env/reward.py:15-31
+//   y_t = close_t / close_{t-1}   data/instrument.py:79
+// keeping the reference association of every fp32 operation (no FMA contraction, IEEE div,
+// expf/logf without fast-math) so values stay within 1e-5 relative over 1,000 compounding steps.
+#pragma once
+#include "pmrl_device.cuh"
+
+namespace pmrl {
+
+struct StatAcc {   // per-thread partial of the PMRL_STAT_* vector (only lane 0 of a warp accumulates)
+    double n = 0, sr = 0, sr2 = 0, sv = 0, slnv = 0, ndone = 0, sepret = 0, seplen = 0;
+    double maxv = -INFINITY, maxnegv = -INFINITY;
+};
+
+struct StepOut {       // warp-uniform result of one env transition
+    int idx_new;       // ring pointer after the step
+    int slot_written;  // ring row that received w' (or -1 on auto-reset)
+    int is_full;
+    int k;             // local step after the call
+    int did_reset;
+    float V, reward;
+    int done;
+};
+
+// Zero the ring of env e and set the all-cash row (weight_buffer.py:46-50).
+__device__ __forceinline__ void ring_reset_warp(float* __restrict__ hist_e, int W, int A, int lane) {
+    const int n = W * A;
+    for (int i = lane; i < n; i += 32) hist_e[i] = (i == 0) ? 1.0f : 0.0f;
+}
+
+template <int NPL>
+__device__ __forceinline__ void env_step_warp(const StepParams& p, int e, int lane,
+                                              float (&wn)[NPL], StepOut& out, StatAcc& acc) {
+    const int A = p.A, W = p.W;
+    const size_t eA = (size_t)e * A;
+
+    // ---- state ----
+    float V = p.value[e];
+    int i = p.idx[e];
+    int full = p.is_full[e];
+    int k = p.t[e];
+    const int t0e = p.t0 ? p.t0[e] : 0;
+    float* __restrict__ hist_e = p.hist + (size_t)e * W * A;
+
+    // ---- auto-reset instead of a step (train/on_policy.py:60-61) ----
+    if (p.episode_len > 0 && k >= p.episode_len) {
+        ring_reset_warp(hist_e, W, A, lane);
+        if (lane == 0) {
+            p.value[e] = p.initial_cash;
+            p.idx[e] = 1; p.is_full[e] = 0; p.t[e] = 0;
+            p.reward[e] = 0.0f; p.done[e] = 0;
+            if (p.sharpe) { p.sharpe[3 * (size_t)e] = 0.0; p.sharpe[3 * (size_t)e + 1] = 0.0; p.sharpe[3 * (size_t)e + 2] = 0.0; }
+            if (p.ep_return) p.ep_return[e] = 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) wn[j] = (lane + 32 * j == 0) ? 1.0f : 0.0f;
+        out.idx_new = 1; out.slot_written = -1; out.is_full = 0; out.k = 0; out.did_reset = 1;
+        out.V = p.initial_cash; out.reward = 0.0f; out.done = 0;
+        return;
+    }
+
+    const int k_new = k + 1;
+
+    // ---- inputs: raw action, price relative, previous weights (all loads issued before use) ----
+    float a_raw[NPL], y[NPL], wl[NPL];
+    const bool need_wl = p.commission > 0.0f;
+    const int last_slot = (i - 1 + W) % W;                       // weight_buffer.py:30
+    if (p.y_ext) {
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int a = lane + 32 * j;
+            y[j] = (a < A) ? ld_stream(p.y_ext + eA + a) : 0.0f;
+        }
+    } else {
+        const size_t row = (size_t)(t0e + k_new + W - 1);        // y of the window's last row
+        const float* __restrict__ c1 = p.close_tm + row * A;
+        const float* __restrict__ c0 = c1 - A;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int a = lane + 32 * j;
+            y[j] = (a < A) ? __fdiv_rn(__ldg(c1 + a), __ldg(c0 + a)) : 0.0f;   // instrument.py:79
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        const int a = lane + 32 * j;
+        a_raw[j] = (a < A) ? ld_stream(p.actions + eA + a) : 0.0f;
+        wl[j] = (need_wl && a < A) ? hist_e[(size_t)last_slot * A + a] : 0.0f;
+    }
+
+    // ---- normalise (trading_env.py:58-60; quirks Q1-Q3) ----
+    float s = 0.0f, mn = INFINITY;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        const int a = lane + 32 * j;
+        if (a < A) { s = __fadd_rn(s, a_raw[j]); mn = nanmin(mn, a_raw[j]); }
+    }
+    s = warp_sum(s);
+    mn = warp_min_nan(mn);
+    const bool strict = (p.flags & PMRL_FLAG_STRICT_REFERENCE) != 0;
+    const bool not_close = !isclose_one(s);
+    const bool has_neg = mn < 0.0f;
+    const bool normalise = strict ? (not_close && has_neg) : (not_close || has_neg);
+    float w[NPL];
+    if (normalise) {
+        float mx = 0.0f;
+        if (!strict) {                                           // stabilised softmax (agent/pg/pg.py:53)
+            mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) if (lane + 32 * j < A) mx = fmaxf(mx, a_raw[j]);
+            mx = warp_max(mx);
+        }
+        float se = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int a = lane + 32 * j;
+            w[j] = (a < A) ? expf(__fsub_rn(a_raw[j], mx)) : 0.0f;
+            se = __fadd_rn(se, w[j]);
+        }
+        se = warp_sum(se);
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) w[j] = __fdiv_rn(w[j], se);
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) w[j] = a_raw[j];
+    }
+
+    // ---- transaction remainder factor mu (trading_env.py:67-75; upstream PGPortfolio relu form) ----
+    const float V_prev = V;
+    if (need_wl) {
+        const float c = p.commission;
+        const float w0 = __shfl_sync(PMRL_FULL_MASK, w[0], 0);
+        const float wl0 = __shfl_sync(PMRL_FULL_MASK, wl[0], 0);
+        const float denom = __fsub_rn(1.0f, __fmul_rn(c, w0));
+        const float cw = __fmul_rn(c, wl0);
+        float mu_last = 1.0f, mu = p.mu0;
+        int it = 0;
+        while (fabsf(__fsub_rn(mu, mu_last)) > 1e-10f && it < p.mu_max_iter) {
+            mu_last = mu;
+            float part = 0.0f;
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) {
+                const int a = lane + 32 * j;
+                if (a >= 1 && a < A) part = __fadd_rn(part, fmaxf(__fsub_rn(wl[j], __fmul_rn(mu, w[j])), 0.0f));
+            }
+            part = warp_sum(part);
+            const float numer = __fsub_rn(__fsub_rn(1.0f, cw), __fmul_rn(p.c2, part));
+            mu = __fdiv_rn(numer, denom);
+            ++it;
+        }
+        V = __fmul_rn(mu, V);                                    // trading_env.py:75
+    }
+
+    // ---- value, drift, return (trading_env.py:78-90) ----
+    float port[NPL], part = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        const int a = lane + 32 * j;
+        port[j] = (a < A) ? __fmul_rn(V, __fmul_rn(w[j], y[j])) : 0.0f;
+        part = __fadd_rn(part, port[j]);
+    }
+    const float Vn = warp_sum(part);
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) wn[j] = __fdiv_rn(port[j], Vn);
+    const float ret = __fdiv_rn(Vn, V);
+
+    // ---- ring write (weight_buffer.py:21-26) ----
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        const int a = lane + 32 * j;
+        if (a < A) hist_e[(size_t)i * A + a] = wn[j];
+    }
+    const int i_new = (i + 1 == W) ? 0 : i + 1;
+    if (i_new == 0) full = 1;
+
+    // ---- reward (trading_env.py:99; env/reward.py:15-31) ----
+    float r;
+    if (p.reward_mode == PMRL_REWARD_STEP_LOG) {
+        r = __fmul_rn(logf(ret), p.reward_scale);
+    } else if (p.reward_mode == PMRL_REWARD_RETURNS) {
+        r = __fmul_rn(__fdiv_rn(Vn, V_prev), p.reward_scale);
+    } else if (p.reward_mode == PMRL_REWARD_LOG_RETURNS) {
+        r = __fmul_rn(logf(__fdiv_rn(Vn, V_prev)), p.reward_scale);
+    } else {  // running Sharpe over the episode's value history, fp64 like numpy (reward.py:26-31)
+        r = 0.0f;
+        if (lane == 0) {
+            double* sh = p.sharpe + 3 * (size_t)e;
+            double n = sh[0], mean = sh[1], m2 = sh[2];
+            const double g = (double)Vn / (double)V_prev;
+            n += 1.0;
+            const double d1 = g - mean;
+            mean += d1 / n;
+            m2 += d1 * (g - mean);
+            sh[0] = n; sh[1] = mean; sh[2] = m2;
+            const double sd = sqrt(m2 / (n - 1.0));              // ddof=1 → NaN at n == 1 (quirk Q11)
+            r = (float)(((mean - (double)p.risk_free) / sd) * (double)p.reward_scale);
+        }
+        r = __shfl_sync(PMRL_FULL_MASK, r, 0);
+    }
+
+    const int dn = (p.episode_len > 0 && k_new == p.episode_len) ? 1 : 0;
+    if (lane == 0) {
+        p.value[e] = Vn;
+        p.idx[e] = i_new; p.is_full[e] = (uint8_t)full; p.t[e] = k_new;
+        p.reward[e] = r; p.done[e] = (uint8_t)dn;
+        float epr = 0.0f;
+        if (p.ep_return) { epr = __fadd_rn(p.ep_return[e], r); p.ep_return[e] = epr; }
+        if (p.stats) {
+            acc.n += 1.0; acc.sr += r; acc.sr2 += (double)r * r; acc.sv += Vn; acc.slnv += log((double)Vn);
+            if (dn) { acc.ndone += 1.0; acc.sepret += epr; acc.seplen += k_new; }
+            acc.maxv = fmax(acc.maxv, (double)Vn); acc.maxnegv = fmax(acc.maxnegv, -(double)Vn);
+        }
+    }
+    out.idx_new = i_new; out.slot_written = i; out.is_full = full; out.k = k_new; out.did_reset = 0;
+    out.V = Vn; out.reward = r; out.done = dn;
+}
+
+// Block-level flush of the per-warp StatAcc partials: warp leaders → smem → thread 0 → 10 atomics.
+__device__ __forceinline__ void stats_flush_block(const StatAcc& acc, double* __restrict__ stats,
+                                                  double* sm /* [warps*10] */, int lane, int warp, int nwarps) {
+    if (lane == 0) {
+        double* s = sm + warp * PMRL_STATS_LEN;
+        s[0] = acc.n; s[1] = acc.sr; s[2] = acc.sr2; s[3] = acc.sv; s[4] = acc.slnv;
+        s[5] = acc.ndone; s[6] = acc.sepret; s[7] = acc.seplen; s[8] = acc.maxv; s[9] = acc.maxnegv;
+    }
+    __syncthreads();
+    if (threadIdx.x < PMRL_STATS_LEN) {
+        const int q = threadIdx.x;
+        double v = sm[q];
+        for (int wi = 1; wi < nwarps; ++wi) {
+            const double o = sm[wi * PMRL_STATS_LEN + q];
+            v = (q >= PMRL_STAT_MAX_V) ? fmax(v, o) : v + o;
+        }
+        if (q >= PMRL_STAT_MAX_V) { if (v > -INFINITY) atomic_max_double(stats + q, v); }
+        else if (v != 0.0) atomicAdd(stats + q, v);
+    }
+}
+
+}  // namespace pmrl

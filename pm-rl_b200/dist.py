@@ -1,0 +1,47 @@
+"""Multi-GPU plumbing: one process per GPU, the env batch sharded by contiguous slices, no data-path
+collective.  The only exchange is the all-reduce of the 10-double statistics vector (NCCL over NVLink on
+the GPU box, gloo in the CPU tests)."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+N_SUM_STATS = 8     # entries [0, 8) are sums, [8, 10) are maxima (include/pmrl_b200.h PMRL_STAT_*)
+
+
+def shard_range(num_envs_global: int, rank: int, world: int) -> tuple[int, int]:
+    """Rank r owns global envs [r*E/R, (r+1)*E/R); E must divide evenly."""
+    if num_envs_global % world != 0:
+        raise ValueError(f"num_envs {num_envs_global} is not divisible by world size {world}")
+    per = num_envs_global // world
+    return rank * per, (rank + 1) * per
+
+
+def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
+    """Initialise the default process group from torchrun's env (RANK/WORLD_SIZE/LOCAL_RANK/MASTER_*).
+    Returns (rank, world, local_rank); a single-process run needs no process group."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local_rank
+
+
+def all_reduce_stats(stats: torch.Tensor) -> torch.Tensor:
+    """SUM over the first 8 entries, MAX over the last 2; identity without a process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return stats
+    sums = stats[:N_SUM_STATS].clone()
+    maxs = stats[N_SUM_STATS:].clone()
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
+    return torch.cat([sums, maxs])

@@ -1,0 +1,202 @@
+"""BatchedTradingEnv — E lockstep portfolio environments on one B200, driven through the C-ABI.
+
+Keeps the reference env's reset/step contract (env/sim/trading_env.py:21-105) batched over E:
+
+    obs = env.reset()                       # [E, A, W, F]   (TradingEnv.reset, :21-41)
+    obs, reward, done = env.step(actions)   # actions [E, A] (TradingEnv.step,  :44-105)
+
+All state lives in device tensors owned by torch; the kernels only borrow the pointers for the
+enqueued work.  Nothing here syncs with the host; `stats()` is the only call that reads back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .config import EnvConfig
+
+OBS_NONE, OBS_FULL, OBS_WEIGHTS = 0, 1, 2
+STATS_LEN = 10
+STAT_NAMES = ("n_envs", "sum_r", "sum_r2", "sum_v", "sum_lnv", "n_done", "sum_ep_return", "sum_ep_len",
+              "max_v", "max_neg_v")
+
+
+def _as_f32_cuda(x, device):
+    t = torch.as_tensor(x)
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+class BatchedTradingEnv:
+    """E independent `TradingEnv`s advanced by one fused CUDA launch per step.
+
+    Args:
+        cfg:       EnvConfig (reference config surface).
+        prices:    [T, A, C] price table (OHLC; `close_channel` selects the close used for
+                   y_t = close_t / close_{t-1}, data/instrument.py:79), or None if every step gets `y=`.
+        features:  [T, A, F-1] feature table gathered into the obs window (defaults to `prices` when its
+                   channel count is F-1); FFD'ed / scaled tables come from `pmrl_b200.features`.
+        t0:        [E] int episode offsets into the table (default 0).
+        collect_stats: accumulate the PMRL_STAT_* vector on device every step.
+    """
+
+    def __init__(self, cfg: EnvConfig, prices=None, features=None, t0=None, close_channel: int = 3,
+                 device=None, collect_stats: bool = False):
+        if not torch.cuda.is_available():
+            raise _lib.PmrlError("BatchedTradingEnv needs a CUDA device (pmrl_b200 has no CPU fallback)")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        E, A, W, F = cfg.num_envs, cfg.num_assets, cfg.window_size, cfg.num_features
+        self.E, self.A, self.W, self.F = E, A, W, F
+        dev = self.device
+        self.close_tm = None
+        self.feat_am = None
+        self.T = 0
+        if prices is not None:
+            p = _as_f32_cuda(prices, dev)
+            if p.dim() != 3 or p.shape[1] != A:
+                raise ValueError(f"prices must be [T, {A}, C], got {tuple(p.shape)}")
+            self.T = p.shape[0]
+            self.close_tm = p[:, :, close_channel].contiguous()                  # [T, A]
+            if features is None and p.shape[2] == F - 1:
+                features = p
+        if features is not None:
+            f = _as_f32_cuda(features, dev)
+            if f.dim() != 3 or f.shape[1] != A or f.shape[2] != F - 1:
+                raise ValueError(f"features must be [T, {A}, {F - 1}], got {tuple(f.shape)}")
+            if self.T and f.shape[0] != self.T:
+                raise ValueError("prices and features must have the same number of rows")
+            self.T = f.shape[0]
+            self.feat_am = f.permute(1, 0, 2).contiguous()                       # [A, T, F-1]
+        if t0 is None:
+            self.t0 = torch.zeros(E, dtype=torch.int32, device=dev)
+        else:
+            self.t0 = torch.as_tensor(t0).to(device=dev, dtype=torch.int32).contiguous()
+            if self.t0.shape != (E,):
+                raise ValueError(f"t0 must be [{E}]")
+        if self.T:
+            need = int(self.t0.max().item()) + cfg.episode_len + W if E else 0
+            if need > self.T:
+                raise ValueError(f"table too short: max(t0) + episode_len + W = {need} > T = {self.T}")
+            if E and int(self.t0.min().item()) < 0:
+                raise ValueError("t0 must be >= 0")
+            if W < 2 and E and int(self.t0.min().item()) < 1:
+                raise ValueError("W == 1 needs t0 >= 1 (y needs the previous close)")
+        # ---- state ----
+        self.value = torch.empty(E, dtype=torch.float32, device=dev)
+        self.hist = torch.empty(E, W, A, dtype=torch.float32, device=dev)
+        self.idx = torch.empty(E, dtype=torch.int32, device=dev)
+        self.is_full = torch.empty(E, dtype=torch.uint8, device=dev)
+        self.t = torch.empty(E, dtype=torch.int32, device=dev)
+        self.sharpe = torch.zeros(E, 3, dtype=torch.float64, device=dev) if cfg.reward_mode == 3 else None
+        self.ep_return = torch.zeros(E, dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(E, dtype=torch.float32, device=dev)
+        self.done = torch.zeros(E, dtype=torch.uint8, device=dev)
+        self._stats = None
+        if collect_stats:
+            self._stats = torch.zeros(STATS_LEN, dtype=torch.float64, device=dev)
+            self.clear_stats()
+        self._obs = None
+        # ---- C structs (built once; the hot call only passes pointers) ----
+        self._c_cfg = _lib.PmrlEnvCfg(E, A, W, F, self.T, cfg.episode_len, cfg.reward_mode, cfg.mu_max_iter,
+                                      1 if cfg.strict_reference else 0, cfg.initial_cash, cfg.commission,
+                                      cfg.reward_scale, cfg.risk_free_rate)
+        self._c_tbl = _lib.PmrlTables(_lib.ptr(self.close_tm), _lib.ptr(self.feat_am))
+        self._c_st = _lib.PmrlEnvState(_lib.ptr(self.value), _lib.ptr(self.hist), _lib.ptr(self.idx),
+                                       _lib.ptr(self.is_full), _lib.ptr(self.t), _lib.ptr(self.t0),
+                                       _lib.ptr(self.sharpe), _lib.ptr(self.ep_return))
+        self._p_cfg, self._p_tbl, self._p_st = C.byref(self._c_cfg), C.byref(self._c_tbl), C.byref(self._c_st)
+        self.reset(obs=False)
+
+    # ------------------------------------------------------------------------------------------
+    def _obs_buffer(self, out):
+        if out is not None:
+            if out.shape != (self.E, self.A, self.W, self.F) or out.dtype != torch.float32:
+                raise ValueError(f"obs out must be float32 [{self.E}, {self.A}, {self.W}, {self.F}]")
+            return out
+        if self._obs is None:
+            self._obs = torch.empty(self.E, self.A, self.W, self.F, dtype=torch.float32, device=self.device)
+        return self._obs
+
+    def reset(self, mask=None, obs: bool = True, out=None):
+        """TradingEnv.reset batched (trading_env.py:21-41): re-initialise the masked envs (all if None).
+        Returns the obs buffer [E, A, W, F] (rows of unmasked envs are left untouched) or None."""
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+        want_obs = obs and self.feat_am is not None
+        buf = self._obs_buffer(out) if want_obs else None
+        rc = self.lib.pmrl_env_reset(self._p_cfg, self._p_tbl, self._p_st, _lib.ptr(m), _lib.ptr(buf),
+                                     OBS_FULL if want_obs else OBS_NONE, _lib.current_stream())
+        _lib.check(rc, "pmrl_env_reset")
+        return buf
+
+    def step(self, actions, y=None, obs: bool = True, out=None):
+        """TradingEnv.step batched (trading_env.py:44-105).
+
+        actions [E, A] (raw scores or weights; also accepts [E, A, 1]); y: optional external price
+        relatives [E, A] (else computed from the close table).  Returns (obs | None, reward [E], done [E] u8);
+        the returned tensors are the env's own buffers and are overwritten by the next step."""
+        a = actions
+        if a.dtype != torch.float32 or not a.is_cuda:
+            a = a.to(device=self.device, dtype=torch.float32)
+        a = a.reshape(self.E, self.A).contiguous()
+        if y is not None:
+            y = y.to(device=self.device, dtype=torch.float32).reshape(self.E, self.A).contiguous()
+        want_obs = obs and self.feat_am is not None
+        buf = self._obs_buffer(out) if want_obs else None
+        rc = self.lib.pmrl_env_step(self._p_cfg, self._p_tbl, self._p_st, a.data_ptr(), _lib.ptr(y),
+                                    self.reward.data_ptr(), self.done.data_ptr(), _lib.ptr(buf),
+                                    OBS_FULL if want_obs else OBS_NONE, _lib.ptr(self._stats),
+                                    _lib.current_stream())
+        _lib.check(rc, "pmrl_env_step")
+        return buf, self.reward, self.done
+
+    def write_weight_channel(self, obs):
+        """features[:, :, -1] = weights.get_all() on a caller-filled obs [E, A, W, F] (trading_env.py:103)."""
+        rc = self.lib.pmrl_obs_build(self._p_cfg, self._p_tbl, self._p_st, _lib.ptr(obs), OBS_WEIGHTS,
+                                     _lib.current_stream())
+        _lib.check(rc, "pmrl_obs_build")
+        return obs
+
+    def observe(self, out=None):
+        """Materialise the obs of the current state without stepping."""
+        buf = self._obs_buffer(out)
+        rc = self.lib.pmrl_obs_build(self._p_cfg, self._p_tbl, self._p_st, _lib.ptr(buf), OBS_FULL,
+                                     _lib.current_stream())
+        _lib.check(rc, "pmrl_obs_build")
+        return buf
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def weights_last(self):
+        """ActionBuffer.get_last batched (weight_buffer.py:28-30) → [E, A]."""
+        last = ((self.idx.long() - 1) % self.W)
+        return self.hist[torch.arange(self.E, device=self.device), last]
+
+    def clear_stats(self):
+        if self._stats is not None:
+            self._stats.zero_()
+            self._stats[8:] = float("-inf")
+
+    def stats(self, all_reduce: bool = False, clear: bool = True):
+        """Read the device statistics vector (one host sync).  With all_reduce=True the vector is first
+        summed (max for the extrema) across the ranks of the default process group."""
+        if self._stats is None:
+            raise _lib.PmrlError("construct the env with collect_stats=True")
+        v = self._stats.clone()
+        if all_reduce:
+            from .dist import all_reduce_stats
+            v = all_reduce_stats(v)
+        h = v.cpu().tolist()
+        if clear:
+            self.clear_stats()
+        d = dict(zip(STAT_NAMES, h))
+        n = max(d["n_envs"], 1.0)
+        d["mean_reward"] = d["sum_r"] / n
+        d["mean_value"] = d["sum_v"] / n
+        d["min_v"] = -d.pop("max_neg_v")
+        d["mean_ep_return"] = d["sum_ep_return"] / max(d["n_done"], 1.0)
+        return d
