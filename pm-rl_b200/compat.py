@@ -1,0 +1,157 @@
+"""Drop-in `TradingEnv` (E = 1) with the reference's exact call surface, executing on the CUDA kernels.
+
+Mirrors env/sim/trading_env.py:7-105 so that `train/on_policy.py:_rollout`, `train/off_policy.py:_collect`
+and `agent/pg` drive it unchanged:
+
+    env = TradingEnv()                       # shapes from config.base like the reference (or an EnvConfig)
+    s = env.reset(features)                  # features [A, W, F], last channel overwritten in place
+    r, s_ = env.step(action, features, prices)
+    env.value, env.weights.get_last(), env.weights.get_all(), env.info["values"|"actions"|"rewards"|"returns"]
+
+`features` / `prices` are supplied by the caller exactly as in the reference (the loader owns the
+windows), so the kernels run with external price relatives and only write the weight channel
+(PMRL_OBS_WEIGHTS).  CPU tensors are staged through the device; there is no CPU compute path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import EnvConfig
+from .env import BatchedTradingEnv
+
+
+class _WeightsView:
+    """ActionBuffer read surface (env/sim/weight_buffer.py:28-44) over the device ring."""
+
+    def __init__(self, owner):
+        self._o = owner
+
+    @property
+    def buffer(self):
+        return self._o._env.hist[0]                       # [W, A]
+
+    @property
+    def idx(self):
+        return int(self._o._env.idx[0].item())
+
+    @property
+    def is_full(self):
+        return bool(self._o._env.is_full[0].item())
+
+    def get_last(self):
+        return self._o._env.weights_last[0]               # [A]
+
+    def get_all(self):
+        e = self._o._env
+        # the WEIGHTS-mode kernel on a scratch [1, A, W, F] tensor; its last channel is get_all()
+        scratch = torch.zeros(1, e.A, e.W, e.F, dtype=torch.float32, device=e.device)
+        e.write_weight_channel(scratch)
+        return scratch[0, :, :, -1]                       # [A, W]
+
+
+class _RewardView:
+    """Reward.* (env/reward.py:15-31) evaluated from the device-side value trace."""
+
+    def __init__(self, owner):
+        self._o = owner
+
+    def _values(self):
+        return self._o.info["values"]
+
+    def returns(self):
+        v = self._values()
+        return np.float32(v[-1]) / np.float32(v[-2])
+
+    def log_returns(self):
+        return np.log(self.returns())
+
+    def sharpe_ratio(self):
+        v = np.array(self._values(), dtype=np.float64)
+        g = v[1:] / v[:-1]
+        with np.errstate(all="ignore"):
+            return (np.mean(g) - self._o.cfg.risk_free_rate) / np.std(g, ddof=1)
+
+    def get_reward(self):
+        name = self._o.reward_name
+        fn = {"returns": self.returns, "log_returns": self.log_returns, "sharpe_ratio": self.sharpe_ratio}[name]
+        return self._o.cfg.reward_scale * fn()
+
+
+class TradingEnv:
+    def __init__(self, cfg: EnvConfig | None = None, device=None, three_tuple: bool = False):
+        if cfg is None:
+            try:
+                cfg = EnvConfig.from_reference_config()
+                import config.base as cb
+                self.reward_name = getattr(cb, "REWARD", "log_returns")
+            except ImportError:
+                cfg = EnvConfig()
+                self.reward_name = "log_returns"
+        else:
+            self.reward_name = cfg.reward if cfg.reward != "step_log" else "log_returns"
+        # a single env, never "done" (the reference ends an episode at loader exhaustion), step reward = :99
+        self.cfg = EnvConfig(**{**cfg.__dict__, "num_envs": 1, "episode_len": 0, "reward": "step_log"})
+        self._env = BatchedTradingEnv(self.cfg, prices=None, features=None, device=device)
+        self.init_cash = self.cfg.initial_cash            # agent/dreamer/dreamer.py:197
+        self.three_tuple = three_tuple
+        self.weights = _WeightsView(self)
+        self.reward = _RewardView(self)
+        self._trace = None
+        self._clear_trace()
+
+    # -- info: the reference appends host copies every step (:80,85,90,100); here the trace stays on the
+    #    device and is materialised only when `info` is read --
+    def _clear_trace(self):
+        self._trace = {"values": [], "actions": [], "rewards": [], "returns": []}
+        self._first_action = self._env.weights_last[0].clone()
+
+    @property
+    def info(self):
+        t = self._trace
+        vals = [float(self.cfg.initial_cash)] + ([] if not t["values"] else torch.stack(t["values"]).cpu().tolist())
+        acts = [self._first_action.cpu().numpy()] + [a for a in (torch.stack(t["actions"]).cpu().numpy() if t["actions"] else [])]
+        rews = [0] + ([] if not t["rewards"] else torch.stack(t["rewards"]).cpu().tolist())
+        rets = [0] + ([] if not t["returns"] else torch.stack(t["returns"]).cpu().tolist())
+        return {"values": vals, "actions": acts, "rewards": rews, "returns": rets}
+
+    @property
+    def value(self):
+        return self._env.value[0]
+
+    def _write_weights(self, features):
+        A, W, F = self._env.A, self._env.W, self._env.F
+        if tuple(features.shape[-3:]) != (A, W, F):
+            raise ValueError(f"features must be [{A}, {W}, {F}], got {tuple(features.shape)}")
+        if features.is_cuda and features.dtype == torch.float32 and features.is_contiguous():
+            self._env.write_weight_channel(features.view(1, A, W, F))
+        else:
+            dev = features.to(device=self._env.device, dtype=torch.float32).contiguous().view(1, A, W, F)
+            self._env.write_weight_channel(dev)
+            features[..., -1] = dev[0, :, :, -1].to(device=features.device, dtype=features.dtype)
+        return features
+
+    def reset(self, features):
+        """trading_env.py:21-41."""
+        self._env.reset(obs=False)
+        self._clear_trace()
+        return self._write_weights(features)
+
+    def step(self, action, features, prices):
+        """trading_env.py:44-105 → (r, features) (or (features, r, done) with three_tuple=True)."""
+        A = self._env.A
+        if action.numel() != A:
+            raise ValueError(f"Action must have shape ({A},), got {tuple(action.shape)}")    # weight_buffer.py:18-19
+        v_before = self._env.value.clone()
+        _, r, done = self._env.step(action.reshape(1, A), y=prices.reshape(1, A), obs=False)
+        t = self._trace
+        t["values"].append(self._env.value[0].clone())
+        t["actions"].append(self._env.weights_last[0].clone())
+        t["rewards"].append(r[0].clone())
+        t["returns"].append((self._env.value / v_before)[0] if self.cfg.commission == 0 else torch.exp(r[0] / self.cfg.reward_scale))
+        features = self._write_weights(features)
+        rr = r[0].clone()
+        if self.three_tuple:
+            return features, rr, done[0].clone()
+        return rr, features

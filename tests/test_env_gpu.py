@@ -1,0 +1,265 @@
+"""GPU parity of the CUDA env path (through the C-ABI) against the golden fixtures and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.env_oracle import OracleEnv
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+REWARD_IDS = {"step_log": 0, "returns": 1, "log_returns": 2, "sharpe_ratio": 3}
+
+
+def _mods():
+    import pmrl_b200
+    from pmrl_b200 import synth
+    from pmrl_b200.env import BatchedTradingEnv
+    return pmrl_b200, synth, BatchedTradingEnv
+
+
+def make_pair(E, A, W, F=5, T=None, episode_len=60, commission=0.0, reward="step_log", seed=1234,
+              strict=True, collect_stats=False, first_env=0):
+    pmrl, synth, Env = _mods()
+    T = T or (W + episode_len + 64)
+    tbl4 = synth.gbm_ohlc(T, A, seed)                       # [T, A, 4] (CPU bits shared by both sides)
+    if F - 1 == 4:
+        feat = tbl4
+    else:                                                   # other channel counts: deterministic mix of OHLC
+        reps = [tbl4[..., i % 4] * (1.0 + 0.25 * (i // 4)) for i in range(F - 1)]
+        feat = torch.stack(reps, dim=-1).contiguous()
+    t0 = synth.episode_offsets(E, T, W, episode_len, first_env=first_env)
+    cfg = pmrl.EnvConfig(num_envs=E, num_assets=A, window_size=W, num_features=F, commission=commission,
+                         reward=reward, episode_len=episode_len, strict_reference=strict)
+    gpu = Env(cfg, prices=tbl4, features=feat, t0=t0, collect_stats=collect_stats)
+    ora = OracleEnv(E, A, W, F, close=tbl4[:, :, 3].numpy(), feat=feat.numpy(), t0=t0.numpy(),
+                    episode_len=episode_len, commission=commission, reward_mode=REWARD_IDS[reward],
+                    strict_reference=strict)
+    return gpu, ora
+
+
+def compare_state(gpu, ora, msg=""):
+    np.testing.assert_array_equal(gpu.idx.cpu().numpy(), ora.idx, err_msg=msg)
+    np.testing.assert_array_equal(gpu.is_full.cpu().numpy(), ora.is_full, err_msg=msg)
+    np.testing.assert_array_equal(gpu.t.cpu().numpy(), ora.t, err_msg=msg)
+    util.assert_values_close(gpu.value.cpu().numpy(), ora.value, msg)
+    np.testing.assert_allclose(gpu.hist.cpu().numpy(), ora.hist, rtol=util.RTOL_WEIGHT, atol=util.ATOL_WEIGHT, err_msg=msg)
+
+
+def compare_obs(obs_gpu, ora, msg=""):
+    want = ora.obs()
+    got = obs_gpu.cpu().numpy()
+    F = want.shape[-1]
+    np.testing.assert_array_equal(got[..., : F - 1], want[..., : F - 1], err_msg=msg + " feature window")   # pure gather: bit-exact
+    np.testing.assert_array_equal(got[..., F - 1] == 0, want[..., F - 1] == 0, err_msg=msg + " weight-channel padding")
+    np.testing.assert_allclose(got[..., F - 1], want[..., F - 1], rtol=util.RTOL_WEIGHT, atol=util.ATOL_WEIGHT, err_msg=msg)
+
+
+@pytest.mark.parametrize("name", util.env_fixture_names())
+def test_cuda_replays_reference_rollout(name):
+    """The CUDA path on the exact inputs of the live-reference rollouts (E = 1, external price relatives)."""
+    pmrl, synth, Env = _mods()
+    d = util.load_env_fixture(name)
+    A, W, F, S = d["A"], d["W"], d["F"], d["S"]
+    cfg = pmrl.EnvConfig(num_envs=1, num_assets=A, window_size=W, num_features=F, commission=d["commission"],
+                         episode_len=0)
+    env = Env(cfg)
+    act = torch.from_numpy(d["actions"]).cuda()
+    y = torch.from_numpy(d["y"]).cuda()
+    vals = torch.zeros(S, device="cuda"); rews = torch.zeros(S, device="cuda")
+    idx = torch.zeros(S, dtype=torch.int32, device="cuda"); full = torch.zeros(S, dtype=torch.uint8, device="cuda")
+    wsteps = util.weight_steps(d); snaps = [int(s) for s in d["obs_w_steps"]]
+    wts, obs_w = [], []
+    scratch = torch.zeros(1, A, W, F, device="cuda")
+    reset_w = env.write_weight_channel(scratch.clone())[0, :, :, -1].cpu().numpy()
+    for s in range(S):
+        _, r, _ = env.step(act[s:s + 1], y=y[s:s + 1], obs=False)
+        vals[s] = env.value[0]; rews[s] = r[0]; idx[s] = env.idx[0]; full[s] = env.is_full[0]
+        if s in wsteps:
+            wts.append(env.weights_last[0].clone())
+        if s in snaps:
+            obs_w.append(env.write_weight_channel(scratch.clone())[0, :, :, -1])
+    np.testing.assert_array_equal(idx.cpu().numpy(), d["idx"])
+    np.testing.assert_array_equal(full.cpu().numpy(), d["is_full"])
+    util.assert_values_close(vals.cpu().numpy(), d["values"], name)
+    util.assert_rewards_close(rews.cpu().numpy(), d["rewards"], name)
+    np.testing.assert_allclose(torch.stack(wts).cpu().numpy(), d["weights"], rtol=util.RTOL_WEIGHT, atol=util.ATOL_WEIGHT)
+    got_w = torch.stack(obs_w).cpu().numpy()
+    np.testing.assert_array_equal(got_w == 0, d["obs_w"] == 0)
+    np.testing.assert_allclose(got_w, d["obs_w"], rtol=util.RTOL_WEIGHT, atol=util.ATOL_WEIGHT)
+    np.testing.assert_array_equal(reset_w, d["reset_obs_w"])
+
+
+@pytest.mark.parametrize("A,W,F", [(11, 50, 5), (50, 50, 5), (100, 50, 5), (500, 50, 5), (7, 5, 3), (33, 9, 6), (130, 16, 2)])
+def test_table_driven_step_and_obs_vs_oracle(A, W, F):
+    """Batched, table-driven: window gather, y from the close plane, ring wrap, done and auto-reset."""
+    E, L = 48, W + 7
+    gpu, ora = make_pair(E, A, W, F, episode_len=L)
+    g = torch.Generator().manual_seed(99)
+    obs = gpu.reset()
+    compare_obs(obs, ora, "reset")
+    for s in range(2 * L + 5):
+        act = torch.randn(E, A, generator=g)
+        if s % 7 == 3:
+            act = torch.softmax(act, dim=1)                    # simplex rows → pass-through branch
+        obs, r, done = gpu.step(act.cuda())
+        r_o, d_o = ora.step(act.numpy())
+        np.testing.assert_array_equal(done.cpu().numpy(), d_o, err_msg=f"done @ {s}")
+        util.assert_rewards_close(r.cpu().numpy(), r_o, f"step {s}")
+        compare_state(gpu, ora, f"step {s}")
+        if s < 4 or s % 5 == 0 or (W - 3 <= s % (L + 1) <= W + 2) or s % (L + 1) in (L - 1, L, 0):
+            compare_obs(obs, ora, f"obs @ {s}")
+
+
+@pytest.mark.parametrize("A,seed", [(100, 1), (100, 2), (11, 3), (500, 4)])
+def test_thousand_step_rollout_within_north_star_tolerance(A, seed):
+    """1,000 compounding steps: V, w' within 1e-5 relative, ints bit-exact (BASELINE.json north_star)."""
+    E, W, L = 32, 50, 1000
+    gpu, ora = make_pair(E, A, W, 5, T=W + L + 40, episode_len=L, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    for s in range(L):
+        act = torch.randn(E, A, generator=g)
+        _, r, done = gpu.step(act.cuda(), obs=False)
+        r_o, d_o = ora.step(act.numpy())
+        if s % 100 == 99 or s == L - 1:
+            util.assert_rewards_close(r.cpu().numpy(), r_o, f"step {s}")
+            np.testing.assert_array_equal(done.cpu().numpy(), d_o)
+            compare_state(gpu, ora, f"step {s}")
+    assert done.cpu().numpy().all()
+
+
+@pytest.mark.parametrize("reward", ["returns", "log_returns", "sharpe_ratio"])
+@pytest.mark.parametrize("commission", [0.0, 0.0025])
+def test_reward_variants_and_commission(reward, commission):
+    E, A, W, L = 40, 37, 12, 30
+    gpu, ora = make_pair(E, A, W, 5, episode_len=L, commission=commission, reward=reward)
+    g = torch.Generator().manual_seed(5)
+    for s in range(2 * L + 3):
+        act = torch.randn(E, A, generator=g)
+        _, r, done = gpu.step(act.cuda(), obs=False)
+        r_o, d_o = ora.step(act.numpy())
+        got, want = r.cpu().numpy(), r_o
+        if reward == "sharpe_ratio":
+            np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+            ok = ~np.isnan(want) & (ora.sharpe[:, 0] >= 4)
+            np.testing.assert_allclose(got[ok], want[ok], rtol=5e-4, atol=1e-4)
+        else:
+            util.assert_rewards_close(got, want, f"{reward} step {s}")
+        compare_state(gpu, ora, f"step {s}")
+
+
+def test_commission_large_asset_count():
+    """C5 shape (A = 500, c = 0.0025) on a subsample of envs."""
+    E, A, W, L = 24, 500, 50, 40
+    gpu, ora = make_pair(E, A, W, 5, episode_len=L, commission=0.0025)
+    g = torch.Generator().manual_seed(6)
+    for s in range(L):
+        act = torch.randn(E, A, generator=g)
+        _, r, _ = gpu.step(act.cuda(), obs=False)
+        r_o, _ = ora.step(act.numpy())
+        util.assert_rewards_close(r.cpu().numpy(), r_o, f"step {s}")
+    compare_state(gpu, ora, "end")
+
+
+def test_non_strict_normalisation():
+    E, A, W, L = 16, 20, 8, 20
+    gpu, ora = make_pair(E, A, W, 5, episode_len=L, strict=False)
+    g = torch.Generator().manual_seed(7)
+    for s in range(L):
+        act = torch.rand(E, A, generator=g) * (2.0 if s % 2 else 1.0)     # non-negative, not a simplex
+        _, r, _ = gpu.step(act.cuda(), obs=False)
+        r_o, _ = ora.step(act.numpy())
+        util.assert_rewards_close(r.cpu().numpy(), r_o, f"step {s}")
+    compare_state(gpu, ora, "end")
+
+
+def test_masked_reset_and_observe():
+    E, A, W, L = 20, 13, 6, 50
+    gpu, ora = make_pair(E, A, W, 5, episode_len=L)
+    g = torch.Generator().manual_seed(8)
+    for s in range(9):
+        act = torch.randn(E, A, generator=g)
+        gpu.step(act.cuda(), obs=False); ora.step(act.numpy())
+    mask = (torch.arange(E) % 3 == 0)
+    before = gpu.observe().clone()
+    obs = gpu.reset(mask=mask.cuda())
+    ora.reset(mask.numpy())
+    compare_state(gpu, ora, "after masked reset")
+    want = ora.obs()
+    got = obs.cpu().numpy()
+    m = mask.numpy()
+    np.testing.assert_allclose(got[m], want[m], rtol=util.RTOL_WEIGHT, atol=util.ATOL_WEIGHT)
+    np.testing.assert_array_equal(got[~m], before.cpu().numpy()[~m])        # unmasked rows untouched
+    compare_obs(gpu.observe(), ora, "observe")
+
+
+def test_stats_vector_matches_oracle():
+    E, A, W, L = 300, 21, 8, 11
+    gpu, ora = make_pair(E, A, W, 5, episode_len=L, collect_stats=True)
+    g = torch.Generator().manual_seed(9)
+    tot = dict(n=0.0, sr=0.0, sr2=0.0, sv=0.0, slnv=0.0, nd=0.0, sep=0.0, sel=0.0, mx=-np.inf, mn=np.inf)
+    for s in range(L + 3):
+        act = torch.randn(E, A, generator=g)
+        gpu.step(act.cuda(), obs=False)
+        live = ora.t < L
+        epr_before = ora.ep_return.copy()
+        r_o, d_o = ora.step(act.numpy())
+        r64 = r_o.astype(np.float64)[live]
+        v64 = ora.value.astype(np.float64)[live]
+        tot["n"] += live.sum(); tot["sr"] += r64.sum(); tot["sr2"] += (r64 ** 2).sum()
+        tot["sv"] += v64.sum(); tot["slnv"] += np.log(v64).sum()
+        dn = d_o.astype(bool)
+        tot["nd"] += dn.sum(); tot["sep"] += ora.ep_return[dn].astype(np.float64).sum(); tot["sel"] += ora.t[dn].sum()
+        if live.any():
+            tot["mx"] = max(tot["mx"], v64.max()); tot["mn"] = min(tot["mn"], v64.min())
+    st = gpu.stats()
+    assert st["n_envs"] == tot["n"] and st["n_done"] == tot["nd"] and st["sum_ep_len"] == tot["sel"]
+    np.testing.assert_allclose([st["sum_r"], st["sum_r2"], st["sum_v"], st["sum_lnv"], st["sum_ep_return"]],
+                               [tot["sr"], tot["sr2"], tot["sv"], tot["slnv"], tot["sep"]], rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose([st["max_v"], st["min_v"]], [tot["mx"], tot["mn"]], rtol=1e-5)
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 (4,096 envs x 50 assets x window 50) through size-independent properties."""
+    E, A, W, L = 4096, 50, 50, 64
+    pmrl, synth, Env = _mods()
+    T = 512
+    tbl = synth.gbm_ohlc(T, A)
+    t0 = synth.episode_offsets(E, T, W, L)
+    cfg = pmrl.EnvConfig(num_envs=E, num_assets=A, window_size=W, episode_len=L)
+    env = Env(cfg, prices=tbl, t0=t0)
+    obs = env.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    tblc = tbl.cuda()
+    for s in range(L):
+        v_prev = env.value.clone()
+        act = torch.randn(E, A, generator=g, device="cuda")
+        obs, r, done = env.step(act)
+        w = env.weights_last
+        assert torch.all(w >= 0) and torch.allclose(w.sum(1), torch.ones(E, device="cuda"), atol=2e-6)
+        assert torch.all(env.value > 0)
+        assert torch.allclose(r, torch.log(env.value / v_prev), atol=2e-6)          # reward = ln(V'/V) at c = 0
+        assert torch.equal(env.t, torch.full((E,), s + 1, dtype=torch.int32, device="cuda"))
+        assert torch.equal(env.idx, torch.full((E,), (s + 2) % W, dtype=torch.int32, device="cuda"))
+        assert bool(done.all()) == (s == L - 1)
+        # the obs feature channels are the table window [t0+k, t0+k+W) of every env
+        e = (s * 37) % E
+        r0 = int(t0[e]) + s + 1
+        assert torch.equal(obs[e, :, :, :4], tblc[r0:r0 + W].permute(1, 0, 2))
+        # newest weight column holds w'
+        col = (W - 1) if s + 2 < W else (s + 1) % W
+        assert torch.equal(obs[:, :, col, 4], w)
+
+
+def test_bad_arguments_raise():
+    pmrl, synth, Env = _mods()
+    from pmrl_b200._lib import PmrlError
+    tbl = synth.gbm_ohlc(64, 5)
+    with pytest.raises(ValueError):
+        Env(pmrl.EnvConfig(num_envs=2, num_assets=5, window_size=8, episode_len=100), prices=tbl)      # table too short
+    with pytest.raises(PmrlError):
+        Env(pmrl.EnvConfig(num_envs=2, num_assets=2000, window_size=8, episode_len=0)).step(
+            torch.zeros(2, 2000, device="cuda"), y=torch.ones(2, 2000, device="cuda"))                 # A > 1024
+    env = Env(pmrl.EnvConfig(num_envs=2, num_assets=5, window_size=8, episode_len=0))
+    with pytest.raises(PmrlError):
+        env.step(torch.zeros(2, 5, device="cuda"))                                                    # no table, no y

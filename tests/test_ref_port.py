@@ -1,0 +1,48 @@
+"""oracle/ref_port.py (the CPU-baseline port) against the live reference and the golden fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.ref_port import RefPortEnv
+from tests import util
+
+
+def run_port(d, steps=None):
+    A, W, F = d["A"], d["W"], d["F"]
+    S = steps or d["S"]
+    env = RefPortEnv(A, W, commission=d["commission"])
+    feats = torch.zeros(A, W, F)
+    env.reset(feats.clone())
+    vals = np.zeros(S, np.float32); rews = np.zeros(S, np.float32)
+    for s in range(S):
+        r, obs = env.step(torch.from_numpy(d["actions"][s]).reshape(1, A, 1), feats.clone(), torch.from_numpy(d["y"][s]))
+        vals[s] = float(env.value); rews[s] = float(r)
+    return env, vals, rews, obs
+
+
+@pytest.mark.parametrize("name", [n for n in util.env_fixture_names() if "A500" not in n])
+def test_port_matches_golden(name):
+    d = util.load_env_fixture(name)
+    env, vals, rews, obs = run_port(d)
+    util.assert_values_close(vals, d["values"], name, rtol=2e-6)
+    util.assert_rewards_close(rews, d["rewards"], name)
+    assert env.ring.pos == d["idx"][-1] and env.ring.wrapped == bool(d["is_full"][-1])
+    np.testing.assert_allclose(obs[:, :, -1].numpy(), d["obs_w"][-1], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.needs_reference
+def test_port_is_bit_identical_to_live_reference():
+    from oracle import live_reference as live
+    from tests.golden.make_golden import make_inputs
+    A, W, S = 23, 10, 200
+    te = live.load_env_module(A, W)
+    torch.set_num_threads(1)
+    act, y = make_inputs(77, "raw", S, A)
+    ref = te.TradingEnv(); port = RefPortEnv(A, W)
+    f = torch.zeros(A, W, 5)
+    assert torch.equal(ref.reset(f.clone()), port.reset(f.clone()))
+    for s in range(S):
+        a = torch.from_numpy(act[s]).reshape(1, A, 1); p = torch.from_numpy(y[s])
+        r1, o1 = ref.step(a, f.clone(), p)
+        r2, o2 = port.step(a, f.clone(), p)
+        assert torch.equal(r1, r2) and torch.equal(o1, o2) and torch.equal(ref.value, port.value)
