@@ -116,6 +116,14 @@ typedef struct PmrlEnvState {
 int         pmrl_abi_version(void);
 const char* pmrl_last_error(void);
 
+/* Launch-shape tuning hook (process-wide; for benchmarking the kernel variants, not part of the reference surface).
+ * value <= 0 restores the built-in heuristic. */
+#define PMRL_TUNE_TILE_ROWS   1   /* asset-rows per obs tile of the fused kernel (power of two <= 32) */
+#define PMRL_TUNE_GROUP_ENVS  2   /* envs a CTA advances together (1..8) */
+#define PMRL_TUNE_CTAS_PER_SM 3   /* persistent CTAs per SM */
+#define PMRL_TUNE_FUSED       4   /* 1 (default): fused step+obs kernel; 0: k_env_step followed by k_obs_build */
+int pmrl_set_tuning(int32_t key, int32_t value);
+
 /* Re-initialise the envs with mask[e] != 0 (mask == NULL → all): V ← initial_cash, ring ← 0 with
  * hist[e,0,0] = 1, idx ← 1, is_full ← 0, t ← 0, sharpe/ep_return cleared.  If obs_mode != NONE the
  * obs of the (re)initialised envs is written (window rows [t0, t0+W) + reset weight channel). */

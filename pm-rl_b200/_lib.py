@@ -37,6 +37,7 @@ P = C.POINTER
 SIGNATURES = {
     "pmrl_abi_version": (C.c_int, []),
     "pmrl_last_error": (C.c_char_p, []),
+    "pmrl_set_tuning": (C.c_int, [i32, i32]),
     "pmrl_env_reset": (C.c_int, [P(PmrlEnvCfg), P(PmrlTables), P(PmrlEnvState), c_void_p, c_void_p, i32, c_void_p]),
     "pmrl_env_step": (C.c_int, [P(PmrlEnvCfg), P(PmrlTables), P(PmrlEnvState), c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, i32, c_void_p, c_void_p]),
@@ -110,3 +111,11 @@ def ptr(t) -> int | None:
 def current_stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+TUNE_TILE_ROWS, TUNE_GROUP_ENVS, TUNE_CTAS_PER_SM, TUNE_FUSED = 1, 2, 3, 4
+
+
+def set_tuning(key: int, value: int) -> None:
+    """Launch-shape tuning hook of the fused step kernel (include/pmrl_b200.h PMRL_TUNE_*); value <= 0 → heuristic."""
+    check(load().pmrl_set_tuning(key, value), "pmrl_set_tuning")

