@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=VAL",
+                    help="kernel launch-shape override: rows|group|ctas|fused|fast = int (pmrl_set_tuning)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -163,6 +165,12 @@ def main():
     from pmrl_b200.env import BatchedTradingEnv
 
     rank, world, local_rank = pdist.init_from_env()
+    from pmrl_b200 import _lib
+    tune_keys = {"rows": _lib.TUNE_TILE_ROWS, "group": _lib.TUNE_GROUP_ENVS, "ctas": _lib.TUNE_CTAS_PER_SM,
+                 "fused": _lib.TUNE_FUSED, "fast": _lib.TUNE_FAST_FILL}
+    for kv in args.tune:
+        k, v = kv.split("=")
+        _lib.set_tuning(tune_keys[k], int(v))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
@@ -261,7 +269,7 @@ def main():
             "env_steps_per_s": value / A,
             "config": {"workload": args.workload, "description": desc, "envs_per_gpu": E, "envs_total": world * E,
                        "assets": A, "window": W, "features": F, "commission": commission, "obs_materialised": obs,
-                       "episode_len": EPISODE_LEN, "table_rows": TABLE_ROWS, "preroll_steps": preroll, "actions": "raw N(0,1) scores (softmax branch)",
+                       "episode_len": EPISODE_LEN, "table_rows": TABLE_ROWS, "preroll_steps": preroll, "tune": args.tune, "actions": "raw N(0,1) scores (softmax branch)",
                        "parallelism": f"env-shard x{world}, NCCL stats all-reduce",
                        "l2_policy": "working set per step (obs write + ring) exceeds L2 (126 MB)" if E * A * W * 4 > 126e6
                                     else "working set smaller than L2: L2-resident by construction"},

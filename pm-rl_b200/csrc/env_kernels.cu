@@ -30,13 +30,13 @@ __global__ void __launch_bounds__(kStepThreads) k_env_step(const StepParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kStepWarps + warp;
     const int nw = gridDim.x * kStepWarps;
-    StatAcc acc;
+    if (p.stats) stats_init_block(s_stats, kStepWarps);
     for (int e = gw; e < p.E; e += nw) {
         float wn[NPL];
         StepOut so;
-        env_step_warp<NPL>(p, e, lane, wn, so, acc);
+        env_step_warp<NPL>(p, e, lane, wn, so, s_stats + warp * PMRL_STATS_LEN);
     }
-    if (p.stats) stats_flush_block(acc, p.stats, s_stats, lane, warp, kStepWarps);
+    if (p.stats) stats_flush_block(p.stats, s_stats, kStepWarps);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -101,7 +101,23 @@ constexpr int kMaxGroup = kFusedWarps;
 
 struct GroupEnv { int row0, shift, fresh_slot, pad; };   // per env of the group (phase 1 → phase 2)
 
-template <int NPL, int MINB>
+// Register-staged tile loader of the fast path (F == 5, W <= 64, 32 asset-rows per tile).  A thread owns
+//   features: asset-rows ar = warp + 8*i (i < 4), window rows w = lane + 32*c (c < 2)  → 8 float4 loads
+//   weights : asset-row  ar = lane,               columns     w = warp + 8*j  (j < 8)  → 8 scalar loads
+// All 16 loads of a tile are issued back to back (memory-level parallelism), and the loads of tile i+1 are
+// issued before tile i is handed to the TMA store, so the L2/DRAM latency overlaps the barriers and the store.
+struct TileRegs {
+    float4 fv[4][2];
+    float wv[8];
+};
+
+struct RowCursor {        // (env-in-group, asset) of a running asset-row index, advanced without divisions
+    int el, a;
+    __device__ __forceinline__ void init(int gar, int A) { el = gar / A; a = gar - el * A; }
+    __device__ __forceinline__ void advance(int d, int A) { a += d; while (a >= A) { a -= A; ++el; } }
+};
+
+template <int NPL, int MINB, bool FAST>
 __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const StepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_stats[kFusedWarps * PMRL_STATS_LEN];
@@ -114,7 +130,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_groups = (p.E + G - 1) / G;
     const size_t row_floats = (size_t)W * F;
-    StatAcc acc;
+    if (p.stats) stats_init_block(s_stats, kFusedWarps);
     int buf = 0;
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int e0 = grp * G;
@@ -124,7 +140,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
             const int e = e0 + warp;
             float wn[NPL];
             StepOut so;
-            env_step_warp<NPL>(p, e, lane, wn, so, acc);
+            env_step_warp<NPL>(p, e, lane, wn, so, s_stats + warp * PMRL_STATS_LEN);
 #pragma unroll
             for (int j = 0; j < NPL; ++j) {
                 const int a = lane + 32 * j;
@@ -144,6 +160,92 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
         const int R = ne * A;
         const int ntiles = (R + TA - 1) / TA;
         float* const obs_grp = p.obs + (size_t)e0 * A * row_floats;
+
+        if constexpr (FAST) {
+            const float4* __restrict__ tbl = reinterpret_cast<const float4*>(p.feat_am);
+            const float* __restrict__ hist_g = p.hist + (size_t)e0 * W * A;
+            RowCursor cf, cw;                       // cursors of this thread's first feature row / its weight row
+            cf.init(warp, A);
+            cw.init(lane, A);
+            TileRegs tr;
+            auto load_tile = [&](int r0) {
+                const int nr = min(32, R - r0);
+                RowCursor c = cf;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ar = warp + 8 * i;
+                    if (ar < nr) {
+                        const float4* __restrict__ src = tbl + (size_t)c.a * T + s_env[c.el].row0;
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc) {
+                            const int w = lane + 32 * cc;
+                            if (w < W) tr.fv[i][cc] = __ldg(src + w);
+                        }
+                    }
+                    c.advance(8, A);
+                }
+                if (lane < nr) {
+                    const GroupEnv ge = s_env[cw.el];
+                    const float* __restrict__ base = hist_g + (size_t)cw.el * W * A + cw.a;
+                    const float fresh = s_wnew[cw.el * A + cw.a];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int w = warp + 8 * j;
+                        const int slot = w - ge.shift;
+                        float v = 0.0f;
+                        if (w < W && slot >= 0) v = (slot == ge.fresh_slot) ? fresh : ld_stream(base + (size_t)slot * A);
+                        tr.wv[j] = v;
+                    }
+                }
+                cf.advance(32, A);
+                cw.advance(32, A);
+            };
+            auto spill_tile = [&](float* __restrict__ tile, int r0) {
+                const int nr = min(32, R - r0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ar = warp + 8 * i;
+                    if (ar < nr) {
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc) {
+                            const int w = lane + 32 * cc;
+                            if (w < W) {
+                                float* d = tile + (ar * W + w) * 5;
+                                const float4 v = tr.fv[i][cc];
+                                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                            }
+                        }
+                    }
+                }
+                if (lane < nr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int w = warp + 8 * j;
+                        if (w < W) tile[(lane * W + w) * 5 + 4] = tr.wv[j];
+                    }
+                }
+            };
+            load_tile(0);
+            for (int ti = 0; ti < ntiles; ++ti) {
+                float* const tile = buf ? tile1 : tile0;
+                if (tid == 0) bulk_wait_read<1>();        // the store that last used this buffer has drained
+                __syncthreads();
+                const int r0 = ti * 32;
+                spill_tile(tile, r0);
+                if (ti + 1 < ntiles) load_tile(r0 + 32);  // next tile's loads fly during the barrier + store
+                fence_proxy_async_smem();
+                __syncthreads();
+                const int nr = min(32, R - r0);
+                float* const gdst = obs_grp + (size_t)r0 * row_floats;
+                const int n = nr * W * 5;
+                if (((((uintptr_t)gdst) | ((size_t)n * 4)) & 15) == 0) {
+                    if (tid == 0) { bulk_store_s2g(gdst, tile, (uint32_t)n * 4u); bulk_commit(); }
+                } else {
+                    for (int q = tid; q < n; q += kFusedThreads) gdst[q] = tile[q];
+                }
+                buf ^= 1;
+            }
+        } else {
         for (int ti = 0; ti < ntiles; ++ti) {
             float* const tile = buf ? tile1 : tile0;
             if (tid == 0) bulk_wait_read<1>();            // the store that last used this buffer has drained
@@ -205,9 +307,10 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
             }
             buf ^= 1;
         }
+        }
     }
     if (tid == 0) bulk_wait_read<0>();
-    if (p.stats) stats_flush_block(acc, p.stats, s_stats, lane, warp, kFusedWarps);
+    if (p.stats) stats_flush_block(p.stats, s_stats, kFusedWarps);
 }
 
 }  // namespace pmrl
@@ -308,7 +411,7 @@ static int launch_step_s(const StepParams& p, cudaStream_t s) {
 
 
 // Fused Mode-O launch: tile rows, group size and grid from the shape (tunable through pmrl_set_tuning).
-static int g_tune_rows = 0, g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1;
+static int g_tune_rows = 0, g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1, g_tune_fast = 1;
 
 extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
     switch (key) {
@@ -316,22 +419,35 @@ extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
         case PMRL_TUNE_GROUP_ENVS: g_tune_group = value; return 0;
         case PMRL_TUNE_CTAS_PER_SM: g_tune_ctas_per_sm = value; return 0;
         case PMRL_TUNE_FUSED: g_tune_fused = value; return 0;
+        case PMRL_TUNE_FAST_FILL: g_tune_fast = value; return 0;
         default: return pmrl_fail(PMRL_E_ARG, "unknown tuning key");
     }
 }
 
-template <int NPL, int MINB>
+template <int NPL, int MINB, bool FAST>
 static int launch_fused_t(StepParams& p, size_t smem, int grid, cudaStream_t s) {
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs<NPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs<NPL, MINB, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return pmrl_fail((int)e, "cudaFuncSetAttribute(k_env_step_obs) failed");
         attr_done[dev] = true;
     }
-    k_env_step_obs<NPL, MINB><<<grid, kFusedThreads, smem, s>>>(p);
+    k_env_step_obs<NPL, MINB, FAST><<<grid, kFusedThreads, smem, s>>>(p);
     return pmrl_check_launch("k_env_step_obs");
+}
+
+template <bool FAST>
+static int launch_fused_npl(StepParams& p, size_t smem, int grid, int npl, cudaStream_t s) {
+    switch (npl) {
+        case 1: return launch_fused_t<1, 3, FAST>(p, smem, grid, s);
+        case 2: return launch_fused_t<2, 3, FAST>(p, smem, grid, s);
+        case 4: return launch_fused_t<4, 3, FAST>(p, smem, grid, s);
+        case 8: return launch_fused_t<8, 2, FAST>(p, smem, grid, s);
+        case 16: return launch_fused_t<16, 1, FAST>(p, smem, grid, s);
+        default: return launch_fused_t<32, 1, FAST>(p, smem, grid, s);
+    }
 }
 
 static int launch_fused(StepParams& p, float* obs, int npl, cudaStream_t s) {
@@ -340,6 +456,8 @@ static int launch_fused(StepParams& p, float* obs, int npl, cudaStream_t s) {
     int rows = g_tune_rows > 0 ? g_tune_rows : 32;
     while (rows > 1 && rows * row_bytes > 36 * 1024) rows >>= 1;
     p.tile_assets = rows;
+    // register-staged, software-pipelined fill for the reference obs shape family
+    const bool fast = (p.F == 5) && (p.W <= 64) && (rows == 32) && g_tune_fast;
     int ctas_per_sm = g_tune_ctas_per_sm > 0 ? g_tune_ctas_per_sm : (npl <= 4 ? 3 : (npl <= 8 ? 2 : 1));
     const int slots = pmrl_sm_count() * ctas_per_sm;
     int G = g_tune_group > 0 ? g_tune_group : kMaxGroup;
@@ -350,14 +468,7 @@ static int launch_fused(StepParams& p, float* obs, int npl, cudaStream_t s) {
     if (smem > 200 * 1024) return pmrl_fail(PMRL_E_SHAPE, "fused step: shared-memory budget exceeded");
     const int n_groups = (p.E + G - 1) / G;
     const int grid = n_groups < slots ? n_groups : slots;
-    switch (npl) {
-        case 1: return launch_fused_t<1, 3>(p, smem, grid, s);
-        case 2: return launch_fused_t<2, 3>(p, smem, grid, s);
-        case 4: return launch_fused_t<4, 3>(p, smem, grid, s);
-        case 8: return launch_fused_t<8, 2>(p, smem, grid, s);
-        case 16: return launch_fused_t<16, 1>(p, smem, grid, s);
-        default: return launch_fused_t<32, 1>(p, smem, grid, s);
-    }
+    return fast ? launch_fused_npl<true>(p, smem, grid, npl, s) : launch_fused_npl<false>(p, smem, grid, npl, s);
 }
 
 extern "C" int pmrl_env_reset(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,

@@ -12,10 +12,13 @@
 
 namespace pmrl {
 
-struct StatAcc {   // per-thread partial of the PMRL_STAT_* vector (only lane 0 of a warp accumulates)
-    double n = 0, sr = 0, sr2 = 0, sv = 0, slnv = 0, ndone = 0, sepret = 0, seplen = 0;
-    double maxv = -INFINITY, maxnegv = -INFINITY;
-};
+// Per-warp partial of the PMRL_STAT_* vector lives in shared memory (10 doubles per warp, touched only by
+// lane 0) so that it costs no registers across the long-lived persistent loops.
+__device__ __forceinline__ void stats_init_block(double* sm /* [warps*10] */, int nwarps) {
+    for (int q = threadIdx.x; q < nwarps * PMRL_STATS_LEN; q += blockDim.x)
+        sm[q] = (q % PMRL_STATS_LEN >= PMRL_STAT_MAX_V) ? -INFINITY : 0.0;
+    __syncthreads();
+}
 
 struct StepOut {       // warp-uniform result of one env transition
     int idx_new;       // ring pointer after the step
@@ -35,7 +38,7 @@ __device__ __forceinline__ void ring_reset_warp(float* __restrict__ hist_e, int 
 
 template <int NPL>
 __device__ __forceinline__ void env_step_warp(const StepParams& p, int e, int lane,
-                                              float (&wn)[NPL], StepOut& out, StatAcc& acc) {
+                                              float (&wn)[NPL], StepOut& out, double* __restrict__ acc /* smem [10] of this warp */) {
     const int A = p.A, W = p.W;
     const size_t eA = (size_t)e * A;
 
@@ -211,23 +214,19 @@ __device__ __forceinline__ void env_step_warp(const StepParams& p, int e, int la
         float epr = 0.0f;
         if (p.ep_return) { epr = __fadd_rn(p.ep_return[e], r); p.ep_return[e] = epr; }
         if (p.stats) {
-            acc.n += 1.0; acc.sr += r; acc.sr2 += (double)r * r; acc.sv += Vn; acc.slnv += log((double)Vn);
-            if (dn) { acc.ndone += 1.0; acc.sepret += epr; acc.seplen += k_new; }
-            acc.maxv = fmax(acc.maxv, (double)Vn); acc.maxnegv = fmax(acc.maxnegv, -(double)Vn);
+            acc[PMRL_STAT_N_ENVS] += 1.0; acc[PMRL_STAT_SUM_R] += r; acc[PMRL_STAT_SUM_R2] += (double)r * r;
+            acc[PMRL_STAT_SUM_V] += Vn; acc[PMRL_STAT_SUM_LNV] += log((double)Vn);
+            if (dn) { acc[PMRL_STAT_N_DONE] += 1.0; acc[PMRL_STAT_SUM_EPRET] += epr; acc[PMRL_STAT_SUM_EPLEN] += k_new; }
+            acc[PMRL_STAT_MAX_V] = fmax(acc[PMRL_STAT_MAX_V], (double)Vn);
+            acc[PMRL_STAT_MAX_NEGV] = fmax(acc[PMRL_STAT_MAX_NEGV], -(double)Vn);
         }
     }
     out.idx_new = i_new; out.slot_written = i; out.is_full = full; out.k = k_new; out.did_reset = 0;
     out.V = Vn; out.reward = r; out.done = dn;
 }
 
-// Block-level flush of the per-warp StatAcc partials: warp leaders → smem → thread 0 → 10 atomics.
-__device__ __forceinline__ void stats_flush_block(const StatAcc& acc, double* __restrict__ stats,
-                                                  double* sm /* [warps*10] */, int lane, int warp, int nwarps) {
-    if (lane == 0) {
-        double* s = sm + warp * PMRL_STATS_LEN;
-        s[0] = acc.n; s[1] = acc.sr; s[2] = acc.sr2; s[3] = acc.sv; s[4] = acc.slnv;
-        s[5] = acc.ndone; s[6] = acc.sepret; s[7] = acc.seplen; s[8] = acc.maxv; s[9] = acc.maxnegv;
-    }
+// Block-level flush of the per-warp partials: thread q < 10 folds column q over the warps → 10 atomics per CTA.
+__device__ __forceinline__ void stats_flush_block(double* __restrict__ stats, const double* sm /* [warps*10] */, int nwarps) {
     __syncthreads();
     if (threadIdx.x < PMRL_STATS_LEN) {
         const int q = threadIdx.x;
