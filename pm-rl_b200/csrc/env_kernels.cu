@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
     const int n_groups = (p.E + G - 1) / G;
     const size_t row_floats = (size_t)W * F;
     if (p.stats) stats_init_block(s_stats, kFusedWarps);
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_once = l2_policy_evict_first();
     int buf = 0;
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int e0 = grp * G;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
 #pragma unroll
                         for (int cc = 0; cc < 2; ++cc) {
                             const int w = lane + 32 * cc;
-                            if (w < W) tr.fv[i][cc] = __ldg(src + w);
+                            if (w < W) tr.fv[i][cc] = ld_keep4(src + w, pol_keep);
                         }
                     }
                     c.advance(8, A);
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
                         const int w = warp + 8 * j;
                         const int slot = w - ge.shift;
                         float v = 0.0f;
-                        if (w < W && slot >= 0) v = (slot == ge.fresh_slot) ? fresh : ld_stream(base + (size_t)slot * A);
+                        if (w < W && slot >= 0) v = (slot == ge.fresh_slot) ? fresh : ld_once(base + (size_t)slot * A, pol_once);
                         tr.wv[j] = v;
                     }
                 }
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
                 float* const gdst = obs_grp + (size_t)r0 * row_floats;
                 const int n = nr * W * 5;
                 if (((((uintptr_t)gdst) | ((size_t)n * 4)) & 15) == 0) {
-                    if (tid == 0) { bulk_store_s2g(gdst, tile, (uint32_t)n * 4u); bulk_commit(); }
+                    if (tid == 0) { bulk_store_s2g(gdst, tile, (uint32_t)n * 4u, pol_once); bulk_commit(); }
                 } else {
                     for (int q = tid; q < n; q += kFusedThreads) gdst[q] = tile[q];
                 }
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
                     const float4* __restrict__ src = tbl + (size_t)a * T + s_env[el].row0;
                     float* __restrict__ dst = tile + (size_t)ar * W * 5;
                     for (int w = lane; w < W; w += 32) {
-                        const float4 v = __ldg(src + w);
+                        const float4 v = ld_keep4(src + w, pol_keep);
                         float* d = dst + w * 5;
                         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
                     }
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
                     float* __restrict__ dst = tile + (size_t)ar * W * F;
                     for (int q = lane; q < per; q += 32) {
                         const int w = q / Fm1, c = q - w * Fm1;
-                        dst[w * F + c] = __ldg(src + q);
+                        dst[w * F + c] = ld_keep(src + q, pol_keep);
                     }
                 }
             }
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
                 for (int w = warp; w < W; w += kFusedWarps) {
                     const int slot = w - ge.shift;
                     float v = 0.0f;
-                    if (slot >= 0) v = (slot == ge.fresh_slot) ? fresh : ld_stream(hist_ea + (size_t)slot * A);
+                    if (slot >= 0) v = (slot == ge.fresh_slot) ? fresh : ld_once(hist_ea + (size_t)slot * A, pol_once);
                     dst[w * F] = v;
                 }
             }
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
             float* const gdst = obs_grp + (size_t)r0 * row_floats;
             const int n = nr * W * F;
             if (((((uintptr_t)gdst) | ((size_t)n * 4)) & 15) == 0) {
-                if (tid == 0) { bulk_store_s2g(gdst, tile, (uint32_t)n * 4u); bulk_commit(); }
+                if (tid == 0) { bulk_store_s2g(gdst, tile, (uint32_t)n * 4u, pol_once); bulk_commit(); }
             } else {
                 for (int q = tid; q < n; q += kFusedThreads) gdst[q] = tile[q];
             }

@@ -80,13 +80,14 @@ __device__ __forceinline__ void env_step_warp(const StepParams& p, int e, int la
             y[j] = (a < A) ? ld_stream(p.y_ext + eA + a) : 0.0f;
         }
     } else {
+        const uint64_t pol_keep = l2_policy_evict_last();
         const size_t row = (size_t)(t0e + k_new + W - 1);        // y of the window's last row
         const float* __restrict__ c1 = p.close_tm + row * A;
         const float* __restrict__ c0 = c1 - A;
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
             const int a = lane + 32 * j;
-            y[j] = (a < A) ? __fdiv_rn(__ldg(c1 + a), __ldg(c0 + a)) : 0.0f;   // instrument.py:79
+            y[j] = (a < A) ? __fdiv_rn(ld_keep(c1 + a, pol_keep), ld_keep(c0 + a, pol_keep)) : 0.0f;   // instrument.py:79
         }
     }
 #pragma unroll

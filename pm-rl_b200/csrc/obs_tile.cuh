@@ -16,6 +16,7 @@ namespace pmrl {
 __device__ __forceinline__ void obs_tile_fill_features(const StepParams& p, float* __restrict__ tile,
                                                        int a0, int na, int row0, int tid, int nthreads) {
     const int W = p.W, F = p.F, Fm1 = p.F - 1, T = p.T;
+    const uint64_t pol_keep = l2_policy_evict_last();
     if (Fm1 == 4) {
         // one float4 (o,h,l,c) per (asset,row); consecutive threads walk consecutive rows of one asset:
         // 16-byte coalesced loads of an 800-byte run, stride-5 conflict-free shared stores.
@@ -23,7 +24,7 @@ __device__ __forceinline__ void obs_tile_fill_features(const StepParams& p, floa
         const int n = na * W;
         for (int r = tid; r < n; r += nthreads) {
             const int al = r / W, w = r - al * W;
-            const float4 v = __ldg(tbl + (size_t)(a0 + al) * T + row0 + w);
+            const float4 v = ld_keep4(tbl + (size_t)(a0 + al) * T + row0 + w, pol_keep);
             float* d = tile + r * 5;
             d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         }
@@ -33,7 +34,7 @@ __device__ __forceinline__ void obs_tile_fill_features(const StepParams& p, floa
         for (int q = tid; q < n; q += nthreads) {
             const int al = q / per_asset, rem = q - al * per_asset;
             const int w = rem / Fm1, c = rem - w * Fm1;
-            tile[(al * W + w) * F + c] = __ldg(p.feat_am + ((size_t)(a0 + al) * T + row0) * Fm1 + rem);
+            tile[(al * W + w) * F + c] = ld_keep(p.feat_am + ((size_t)(a0 + al) * T + row0) * Fm1 + rem, pol_keep);
         }
     }
 }
@@ -69,7 +70,7 @@ __device__ __forceinline__ void obs_tile_store(const StepParams& p, const float*
     if (p.obs_mode == PMRL_OBS_FULL) {
         if (p.obs_bulk_ok) {
             if (tid == 0) {
-                bulk_store_s2g(dst, tile, (uint32_t)n * 4u);
+                bulk_store_s2g(dst, tile, (uint32_t)n * 4u, l2_policy_evict_first());
                 bulk_commit();
             }
         } else {

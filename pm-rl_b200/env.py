@@ -41,8 +41,14 @@ class BatchedTradingEnv:
         collect_stats: accumulate the PMRL_STAT_* vector on device every step.
     """
 
+    @classmethod
+    def from_tables(cls, cfg: EnvConfig, close_tm, feat_am, t0=None, device=None, collect_stats: bool = False):
+        """Construct from tables already in the kernel layouts (close_tm [T, A], feat_am [A, T, F-1]), e.g. the
+        output of `pmrl_b200.features.build_env_tables`."""
+        return cls(cfg, t0=t0, device=device, collect_stats=collect_stats, _packed=(close_tm, feat_am))
+
     def __init__(self, cfg: EnvConfig, prices=None, features=None, t0=None, close_channel: int = 3,
-                 device=None, collect_stats: bool = False):
+                 device=None, collect_stats: bool = False, _packed=None):
         if not torch.cuda.is_available():
             raise _lib.PmrlError("BatchedTradingEnv needs a CUDA device (pmrl_b200 has no CPU fallback)")
         self.lib = _lib.load()
@@ -54,6 +60,20 @@ class BatchedTradingEnv:
         self.close_tm = None
         self.feat_am = None
         self.T = 0
+        if _packed is not None:
+            ctm, fam = _packed
+            if ctm is not None:
+                self.close_tm = _as_f32_cuda(ctm, dev)
+                if self.close_tm.dim() != 2 or self.close_tm.shape[1] != A:
+                    raise ValueError(f"close_tm must be [T, {A}]")
+                self.T = self.close_tm.shape[0]
+            if fam is not None:
+                self.feat_am = _as_f32_cuda(fam, dev)
+                if self.feat_am.dim() != 3 or self.feat_am.shape[0] != A or self.feat_am.shape[2] != F - 1:
+                    raise ValueError(f"feat_am must be [{A}, T, {F - 1}]")
+                if self.T and self.feat_am.shape[1] != self.T:
+                    raise ValueError("close_tm and feat_am must have the same number of rows")
+                self.T = self.feat_am.shape[1]
         if prices is not None:
             p = _as_f32_cuda(prices, dev)
             if p.dim() != 3 or p.shape[1] != A:

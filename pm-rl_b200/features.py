@@ -1,0 +1,150 @@
+"""Feature path on device: fractional differencing (data/ffd.py), per-series scaling (data/instrument.py:318-336)
+and packing into the table layouts the env kernels gather from (data/instrument.py:339-356).
+
+`FixedFracDiff` keeps the reference class surface (`FixedFracDiff(data, thres, d_opt).fit_transform()`,
+`get_max_width()`, `get_d_opt`); its `fit` (bisection on a statsmodels ADF p-value, ffd.py:59-78) is host-side,
+one-time and out of scope — `d_opt` must be supplied.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+SCALERS = {"minmax": 0, "standard": 1}
+
+# features the reference leaves untouched (data/ffd.py:21)
+FEAT_IGNORE = ['volume', 'adx', 'adxr', 'apo', 'aroon', 'aroonosc', 'bop', 'cci', 'cmo', 'dx', 'macd', 'macdext', 'macdfix',
+               'mfi', 'minus_di', 'minus_dm', 'mom', 'plus_di', 'plus_dm', 'ppo', 'roc', 'rocp', 'rocr', 'rocr100', 'rsi',
+               'stoch', 'stochf', 'stochrsi', 'trix', 'ultosc', 'willr']
+
+
+def _cuda_f32(x, device=None):
+    t = torch.as_tensor(x)
+    if not t.is_cuda:
+        if not torch.cuda.is_available():
+            raise _lib.PmrlError("the feature path needs a CUDA device (pmrl_b200 has no CPU fallback)")
+        t = t.to(device or "cuda")
+    return t.to(torch.float32).contiguous()
+
+
+def ffd_weights(d, T: int, thres: float, device=None):
+    """Binomial weights + widths per series (ffd.py:38-47).  d: [N] host floats (kept in fp64 like Python floats)."""
+    lib = _lib.load()
+    d64 = torch.as_tensor(np.asarray(d, np.float64)).to(device or "cuda")
+    N = d64.numel()
+    w = torch.empty(N, T, dtype=torch.float32, device=d64.device)
+    widths = torch.empty(N, dtype=torch.int32, device=d64.device)
+    _lib.check(lib.pmrl_ffd_weights(_lib.ptr(d64), N, T, float(thres), _lib.ptr(w), _lib.ptr(widths),
+                                    _lib.current_stream()), "pmrl_ffd_weights")
+    return w, widths, d64
+
+
+def ffd_transform(x, d, thres: float = 1e-5):
+    """FixedFracDiff.transform for a stack of series (ffd.py:80-89).  x: [N, T]; d: [N].
+    Returns (out [N, T - max_width], widths [N] (host ints), max_width).  One host read of the widths sizes the output."""
+    lib = _lib.load()
+    x = _cuda_f32(x)
+    N, T = x.shape
+    w, widths, d64 = ffd_weights(d, T, thres, device=x.device)
+    wh = widths.cpu().numpy()
+    dh = np.asarray(d, np.float64)
+    mw = int(np.where(dh > 0, wh, 0).max()) if N else 0
+    out = torch.empty(N, T - mw, dtype=torch.float32, device=x.device)
+    _lib.check(lib.pmrl_ffd_transform(_lib.ptr(x), _lib.ptr(d64), _lib.ptr(w), _lib.ptr(widths), N, T, mw,
+                                      _lib.ptr(out), _lib.current_stream()), "pmrl_ffd_transform")
+    return out, np.where(dh > 0, wh, 0).astype(np.int32), mw
+
+
+def scale_series(x, method: str = "minmax", out=None):
+    """Instrument.scale per series over its whole length (instrument.py:331-336): sklearn MinMax / Standard semantics."""
+    lib = _lib.load()
+    x = _cuda_f32(x)
+    if out is None:
+        out = torch.empty_like(x)
+    N, L = x.shape
+    _lib.check(lib.pmrl_scale_series(_lib.ptr(x), N, L, SCALERS[method], _lib.ptr(out), _lib.current_stream()),
+               "pmrl_scale_series")
+    return out
+
+
+def pack_tables(series=None, close=None, num_assets: int = 0, channels: int = 0):
+    """series [A*C, L] (index a*C + c) → feat_am [A, L, C]; close [A, L] → close_tm [L, A] (env kernel layouts)."""
+    lib = _lib.load()
+    feat_am = close_tm = None
+    A, C, L = num_assets, channels, 0
+    if series is not None:
+        series = _cuda_f32(series)
+        L = series.shape[1]
+        if series.shape[0] != A * C:
+            raise ValueError(f"series must be [{A * C}, L]")
+        feat_am = torch.empty(A, L, C, dtype=torch.float32, device=series.device)
+    if close is not None:
+        close = _cuda_f32(close)
+        A = A or close.shape[0]
+        L = close.shape[1]
+        close_tm = torch.empty(L, A, dtype=torch.float32, device=close.device)
+    _lib.check(lib.pmrl_pack_features(_lib.ptr(series), _lib.ptr(close), A, max(C, 1), L, _lib.ptr(feat_am),
+                                      _lib.ptr(close_tm), _lib.current_stream()), "pmrl_pack_features")
+    return feat_am, close_tm
+
+
+def build_env_tables(ohlc, d=0.4, thres: float = 1e-5, scaler: str | None = "minmax", close_channel: int = 3):
+    """The reference pipeline FFD → scale → window layout (data/data_loader.py:37-43) for an OHLC table [T, A, C]:
+    every (asset, channel) series is fractionally differenced with `d` (scalar, [C] or [A, C]), scaled over the
+    whole split, and packed to feat_am [A, T', C]; the raw close plane (for y_t) is row-aligned to it → close_tm [T', A].
+    Returns dict(feat_am, close_tm, max_width, rows)."""
+    tbl = _cuda_f32(ohlc)
+    T, A, C = tbl.shape
+    dd = np.broadcast_to(np.asarray(d, np.float64), (A, C)).reshape(-1)
+    series = tbl.permute(1, 2, 0).contiguous().view(A * C, T)          # [A*C, T] series-major (one-time setup copy)
+    out, widths, mw = ffd_transform(series, dd, thres)
+    if scaler is not None:
+        out = scale_series(out, scaler, out=out)
+    close = tbl[mw:, :, close_channel].t().contiguous()                 # [A, T']
+    feat_am, close_tm = pack_tables(out, close, num_assets=A, channels=C)
+    return {"feat_am": feat_am, "close_tm": close_tm, "max_width": mw, "rows": T - mw, "widths": widths}
+
+
+class FixedFracDiff:
+    """data/ffd.py:6-101 surface over the CUDA kernels.  `data`: mapping feature name → 1-D tensor [T]."""
+
+    def __init__(self, data, thres: float = 1e-5, d_opt: dict | None = None):
+        self.data = data
+        self.thres = thres
+        self.len_data = len(next(iter(data.values())))
+        self.feats = [f for f in data.keys() if f not in FEAT_IGNORE]
+        self.d_opt = {f: 0.0 for f in self.feats} if d_opt is None else dict(d_opt)
+        self.widths = [0] * len(self.feats)
+        self._out = None
+
+    def fit(self):
+        missing = [f for f in self.feats if not self.d_opt.get(f, 0.0) > 0.0]
+        if missing:
+            raise NotImplementedError("FixedFracDiff.fit searches d with a statsmodels ADF test (data/ffd.py:59-78), which is "
+                                      f"host-side and out of scope: supply d_opt for {missing}")
+
+    def transform(self):
+        x = torch.stack([torch.as_tensor(self.data[f]).float() for f in self.feats])
+        d = [float(self.d_opt.get(f, 0.0)) for f in self.feats]
+        out, widths, mw = ffd_transform(x, d, self.thres)
+        self.widths = [int(w) for w in widths]
+        res = {k: torch.as_tensor(v)[mw:].clone() for k, v in self.data.items()}
+        host = out.cpu()
+        for i, f in enumerate(self.feats):
+            if d[i] > 0:
+                res[f] = host[i]
+        self._out = res
+        return res
+
+    def fit_transform(self):
+        self.fit()
+        return self.transform()
+
+    def get_max_width(self) -> int:
+        return int(max(self.widths))
+
+    @property
+    def get_d_opt(self) -> dict:
+        return self.d_opt

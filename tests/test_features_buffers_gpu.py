@@ -1,0 +1,232 @@
+"""GPU parity of the feature path, the buffers, the PG reward and the eval metrics (through the C-ABI)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ffd_oracle
+from oracle.buffers_oracle import RolloutOracle, replay_gather
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def golden(name):
+    z = np.load(os.path.join(util.GOLDEN, name))
+    return {k: z[k] for k in z.files}
+
+
+# ---------------------------------------------------------------- FFD / scaling / packing
+def test_ffd_matches_reference_golden():
+    from pmrl_b200 import features
+    g = golden("ffd.npz")
+    w, widths, _ = features.ffd_weights(g["d"], int(g["T"]), float(g["thres"]))
+    np.testing.assert_array_equal(widths.cpu().numpy(), g["widths"])                       # integer: bit-exact
+    ic = list(g["names"]).index("close")
+    wd = int(g["widths"][ic])
+    np.testing.assert_array_equal(w[ic, :wd].flip(0).cpu().numpy(), g["weights_close"])    # sequential fp32 product: bit-exact
+    out, widths2, mw = features.ffd_transform(g["x"], g["d"], float(g["thres"]))
+    assert mw == int(g["max_width"])
+    # conv accumulation order differs from torch's CPU conv1d: fp32 tolerance scaled by the series magnitude (~100)
+    np.testing.assert_allclose(out.cpu().numpy(), g["out"], rtol=1e-5, atol=2e-4)
+    out64 = ffd_oracle.ffd_transform_f64(g["x"], g["d"], float(g["thres"]))
+    err_gpu = np.abs(out.cpu().numpy() - out64).max(); err_ref = np.abs(g["out"] - out64).max()
+    assert err_gpu <= 4 * err_ref + 1e-4, (err_gpu, err_ref)                               # as accurate as the reference's fp32 conv
+
+
+@pytest.mark.parametrize("d,T", [(0.1, 6000), (0.25, 3000), (0.4, 3000), (0.6, 1500), (0.9, 700), (0.0, 300)])
+def test_ffd_vs_oracle_sweep(d, T):
+    from pmrl_b200 import features
+    rs = np.random.RandomState(int(d * 100) + T)
+    x = (100 * np.exp(np.cumsum(0.01 * rs.standard_normal((3, T)), axis=1))).astype(np.float32)
+    dd = np.array([d, d, 0.0])
+    out, widths, mw = features.ffd_transform(x, dd, 1e-4)
+    want, w_o, mw_o = ffd_oracle.ffd_transform(x, dd, 1e-4)
+    assert mw == mw_o and list(widths) == list(w_o)
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-5, atol=3e-4)
+    np.testing.assert_array_equal(out[2].cpu().numpy(), x[2, mw:])                         # d <= 0: passed through untouched
+
+
+@pytest.mark.parametrize("method", ["minmax", "standard"])
+def test_scaling_matches_sklearn(method):
+    from pmrl_b200 import features
+    rs = np.random.RandomState(1)
+    x = (50 + 10 * rs.standard_normal((7, 2111))).astype(np.float32)
+    x[3] = 4.25                                                                            # constant series → scale treated as 1
+    got = features.scale_series(x, method).cpu().numpy()
+    want = ffd_oracle.scale_series(x, method)
+    if method == "minmax":
+        np.testing.assert_array_equal(got, want)                                           # same fp32 op sequence: bit-exact
+    else:
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+
+
+def test_build_env_tables_layout_and_env_consumes_it():
+    import pmrl_b200
+    from pmrl_b200 import features, synth
+    from pmrl_b200.env import BatchedTradingEnv
+    T, A, W, L = 1200, 6, 10, 20
+    tbl = synth.gbm_ohlc(T, A)
+    t = features.build_env_tables(tbl, d=0.6, thres=1e-4, scaler="minmax")
+    mw = t["max_width"]
+    series = tbl.permute(1, 2, 0).reshape(A * 4, T).numpy()
+    want, _, mw_o = ffd_oracle.ffd_transform(series, np.full(A * 4, 0.6), 1e-4)
+    assert mw == mw_o
+    want = ffd_oracle.scale_series(want, "minmax").reshape(A, 4, T - mw).transpose(0, 2, 1)     # [A, T', C]
+    np.testing.assert_allclose(t["feat_am"].cpu().numpy(), want, rtol=1e-4, atol=2e-5)
+    np.testing.assert_array_equal(t["close_tm"].cpu().numpy(), tbl[mw:, :, 3].numpy())
+    # the env gathers its windows from the packed table
+    E = 5
+    cfg = pmrl_b200.EnvConfig(num_envs=E, num_assets=A, window_size=W, episode_len=L)
+    env = BatchedTradingEnv.from_tables(cfg, t["close_tm"], t["feat_am"], t0=torch.arange(E, dtype=torch.int32) * 3)
+    obs = env.reset()
+    for e in range(E):
+        assert torch.equal(obs[e, :, :, :4], t["feat_am"][:, 3 * e:3 * e + W, :])
+
+
+def test_fixedfracdiff_class_surface():
+    from pmrl_b200.features import FixedFracDiff
+    g = golden("ffd.npz")
+    names = [str(n) for n in g["names"]]
+    data = {n: torch.from_numpy(g["x"][i]) for i, n in enumerate(names)}
+    data["volume"] = torch.arange(int(g["T"]), dtype=torch.float32)
+    ffd = FixedFracDiff(data, thres=float(g["thres"]), d_opt={n: float(d) for n, d in zip(names, g["d"])})
+    out = ffd.fit_transform()
+    assert ffd.get_max_width() == int(g["max_width"])
+    for i, n in enumerate(names):
+        np.testing.assert_allclose(out[n].numpy(), g["out"][i], rtol=1e-5, atol=2e-4)
+    np.testing.assert_array_equal(out["volume"].numpy(), np.arange(int(g["T"]), dtype=np.float32)[int(g["max_width"]):])
+    with pytest.raises(NotImplementedError):
+        FixedFracDiff(data, d_opt=None).fit()
+
+
+# ---------------------------------------------------------------- rollout buffer
+def test_rollout_buffer_reproduces_reference_batches():
+    from pmrl_b200.buffers import DeviceRolloutBuffer
+    g = golden("rollout_buffer.npz")
+    A, W, F, L, BS = (int(g[k]) for k in ("A", "W", "F", "L", "BS"))
+    buf = DeviceRolloutBuffer(F, L, 1, A, W, batch_size=BS)
+    buf.set_prices(torch.from_numpy(g["prices"]).t()[W - 1:].reshape(buf.S - 1 + 0, 1, A) if False else
+                   torch.cat([torch.from_numpy(g["prices"]).t()[W - 1:], torch.zeros(buf.S - (L - W + 1), A)]).reshape(buf.S, 1, A))
+    for step in range(1, L):
+        buf.add(torch.from_numpy(g["S"][step]).cuda()[None], torch.from_numpy(g["Act"][step]).cuda().reshape(1, A),
+                torch.tensor([g["V"][step]]).cuda(), torch.tensor([g["R"][step]]).cuda())
+    np.random.seed(11)
+    batches = list(buf.sample_random())
+    assert len(batches) == len(g["idxs"])
+    for b, t in enumerate(batches):
+        for j, name in enumerate(["s", "a", "r", "pv", "pa", "p"]):
+            np.testing.assert_array_equal(t[j].cpu().numpy(), g[f"rand{b}_{name}"], err_msg=f"batch {b} {name}")
+    seq = list(buf.sample())
+    assert len(seq) == int(g["n_seq"])
+    for b, t in enumerate(seq):
+        for j, name in enumerate(["s", "a", "r", "pv", "pa", "p"]):
+            np.testing.assert_array_equal(t[j].cpu().numpy(), g[f"seq{b}_{name}"], err_msg=f"seq {b} {name}")
+
+
+def test_rollout_buffer_batched_direct_obs_write():
+    """The step kernel writes obs straight into the buffer slot; add() appends a / v / r (E > 1)."""
+    import pmrl_b200
+    from pmrl_b200 import synth
+    from pmrl_b200.buffers import DeviceRolloutBuffer
+    from pmrl_b200.env import BatchedTradingEnv
+    E, A, W, F, L = 9, 7, 6, 5, 24
+    tbl = synth.gbm_ohlc(128, A)
+    env = BatchedTradingEnv(pmrl_b200.EnvConfig(num_envs=E, num_assets=A, window_size=W, episode_len=L), prices=tbl)
+    buf = DeviceRolloutBuffer(F, L, E, A, W, batch_size=8)
+    ora = [RolloutOracle(F, L, np.ones((A, L)), A, W, batch_size=8) for _ in range(E)]
+    s = env.reset().clone()
+    g = torch.Generator().manual_seed(2)
+    for step in range(1, L):
+        a = torch.randn(E, A, generator=g).cuda()
+        slot_view = buf.obs_slot()                      # where add() will put s (the obs BEFORE the step, on_policy.py:65)
+        if slot_view is not None:
+            slot_view.copy_(s)
+        s_next, r, _ = env.step(a)
+        buf.add(None if slot_view is not None else s, a, env.value, r)
+        for e in range(E):
+            ora[e].add(s[e].cpu().numpy(), a[e].cpu().numpy(), env.value[e].item(), r[e].item())
+        s = s_next.clone()
+    slots = np.array([1, 5, 7, 12, 18]); envs = np.array([0, 3, 8, 2, 5])
+    got = buf.gather(slots, envs)
+    for b in range(len(slots)):
+        want = ora[envs[b]].batch(np.array([slots[b]]))
+        for j in range(5):                              # s, a, r, _v, _a (prices are unit here)
+            np.testing.assert_allclose(got[j][b].cpu().numpy(), want[j][0], rtol=1e-6, atol=0, err_msg=f"b{b} field {j}")
+
+
+# ---------------------------------------------------------------- index replay
+def test_replay_add_and_gather_vs_oracle():
+    from pmrl_b200.buffers import DeviceReplayBuffer
+    from pmrl_b200 import synth
+    E, A, W, F, train_len = 6, 11, 5, 5, 60
+    tbl = synth.gbm_ohlc(train_len + W + 2, A)
+    feat_am = tbl.permute(1, 0, 2).contiguous().cuda()
+    buf = DeviceReplayBuffer(feat_am, F, train_len, E, A, W, buffer_size=3 * (train_len - 2 * (W - 1)), batch_size=8)
+    P, L = buf.max_epoch, buf.epoch_len
+    bi = np.zeros((P, L, E), np.int32); ba = np.zeros((P, L, E, A), np.float32); br = np.zeros((P, L, E), np.float32)
+    rs = np.random.RandomState(0)
+    for epoch in range(4):                               # wraps around max_epoch = 3
+        for i in range(train_len):
+            a = rs.standard_normal((E, A)).astype(np.float32); r = rs.standard_normal(E).astype(np.float32)
+            buf.add(epoch, i, torch.from_numpy(a).cuda(), torch.from_numpy(r).cuda())
+            st = i - 2 * (W - 1)
+            if i >= W - 1 and 0 <= st < L:
+                bi[epoch % P, st] = i; ba[epoch % P, st] = a; br[epoch % P, st] = r
+    np.testing.assert_array_equal(buf.bi.cpu().numpy(), bi)
+    np.testing.assert_array_equal(buf.ba.cpu().numpy(), ba)
+    assert len(buf) == P
+    epochs = np.array([0, 1, 2, 2, 0]); envs = np.array([0, 5, 2, 3, 1]); starts = np.array([0, 3, L - W - 2, 10, 7])
+    s, a, r, s2 = buf.gather(epochs, envs, starts)
+    for b in range(len(epochs)):
+        ws, wa, wr, ws2 = replay_gather(tbl.numpy(), bi, ba, br, epochs[b], envs[b], starts[b], W)
+        np.testing.assert_array_equal(s[b].cpu().numpy(), ws); np.testing.assert_array_equal(s2[b].cpu().numpy(), ws2)
+        np.testing.assert_array_equal(a[b].cpu().numpy(), wa); np.testing.assert_array_equal(r[b].cpu().numpy(), wr)
+    s, a, r, s2 = buf.sample(torch.Generator().manual_seed(0))
+    assert s.shape == (8, A, W, F) and a.shape == (8, A, 1) and r.shape == (8, 1, 1) and s2.shape == (8, A, W, F)
+
+
+# ---------------------------------------------------------------- PG reward (fwd + grad) and eval metrics
+@pytest.mark.parametrize("mode", ["log_returns", "returns"])
+def test_pg_reward_matches_reference_autograd(mode):
+    from pmrl_b200.pg_reward import pg_reward
+    g = golden("pg_reward.npz")
+    a = torch.from_numpy(g[f"{mode}_a"]).cuda(); pv = torch.from_numpy(g[f"{mode}_pv"]).cuda()
+    pa = torch.from_numpy(g[f"{mode}_pa"]).cuda(); p = torch.from_numpy(g[f"{mode}_p"]).cuda()
+    rew, grad = pg_reward(a, pv, pa, p, mode=mode, normalise=True)
+    np.testing.assert_allclose(rew.mean().item(), float(g[f"{mode}_r"]), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(grad.cpu().numpy(), g[f"{mode}_grad"], rtol=2e-4, atol=2e-8)
+
+
+def test_pg_reward_autograd_function():
+    from pmrl_b200.pg_reward import PGReward
+    B, A = 32, 50
+    a = torch.randn(B, A, 1, device="cuda", requires_grad=True)
+    pv = torch.full((B, 1, 1), 25000.0, device="cuda"); pa = torch.softmax(torch.randn(B, A, 1, device="cuda"), 1)
+    p = 1 + 0.01 * torch.randn(B, A, 1, device="cuda")
+    r = PGReward.apply(a, pv, pa, p, "log_returns", True, 0.0, 1.0)
+    (-r).backward()
+    a2 = a.detach().clone().requires_grad_(True)
+    w = torch.softmax(a2, dim=1)
+    ref = torch.log((pv * (w * p)).sum(1, keepdim=True) / pv).mean()
+    (-ref).backward()
+    np.testing.assert_allclose(r.item(), ref.item(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(a.grad.cpu().numpy(), a2.grad.cpu().numpy(), rtol=2e-4, atol=2e-8)
+
+
+def test_eval_metrics_vs_numpy():
+    from pmrl_b200.metrics import eval_metrics
+    E, N, A = 17, 333, 9
+    rs = np.random.RandomState(2)
+    vals = (25000 * np.exp(np.cumsum(0.01 * rs.standard_normal((E, N)), axis=1))).astype(np.float32)
+    w = rs.random_sample((E, N, A)).astype(np.float32); w /= w.sum(-1, keepdims=True)
+    got = eval_metrics(torch.from_numpy(vals).cuda(), torch.from_numpy(w).cuda(), rf=0.04, periods=252).cpu().numpy()
+    v = vals.astype(np.float64)
+    r = v[:, 1:] / v[:, :-1] - 1 - ((1.04) ** (1 / 252) - 1)
+    sharpe = r.mean(1) / r.std(1, ddof=1) * np.sqrt(252)
+    sortino = r.mean(1) / np.sqrt((np.minimum(r, 0) ** 2).sum(1) / r.shape[1]) * np.sqrt(252)
+    mdd = (v / np.maximum.accumulate(v, axis=1)).min(1) - 1
+    to = np.abs(np.diff(w.astype(np.float64), axis=1)).sum(-1).mean(1)        # util/eval.py:32-37
+    np.testing.assert_allclose(got[:, 0], sharpe, rtol=1e-4); np.testing.assert_allclose(got[:, 1], sortino, rtol=1e-4)
+    np.testing.assert_allclose(got[:, 2], mdd, rtol=1e-5, atol=1e-6); np.testing.assert_allclose(got[:, 3], to, rtol=1e-5)
