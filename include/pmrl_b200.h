@@ -151,7 +151,7 @@ int pmrl_obs_build(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvSt
 
 /* ---- feature path (data/ffd.py, data/instrument.py) ---- */
 
-/* Binomial FFD weights per series: w[n,0]=1, w[n,k]=w[n,k-1]*(1-(d[n]+1)/k) (sequential fp32 product,
+/* Binomial FFD weights per series: w[n,0]=1, w[n,k]=w[n,k-1]*(1-(d[n]+1)/k) (sequential product in a double accumulator rounded to fp32 per prefix, like torch.cumprod on the CPU;
  * ffd.py:38-40; d is a host-precision double like the reference's Python float, rounded to fp32 after
  * the +1); widths[n] = max{k : |w[n,k]| > thres} (ffd.py:43).  d [N] f64 (device), weights [N, T], widths [N] i32. */
 int pmrl_ffd_weights(const double* d, int32_t N, int32_t T, float thres,

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <type_traits>
 #include "pmrl_b200.h"
 #include "pmrl_device.cuh"
 #include "env_step.cuh"
@@ -126,7 +127,8 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
     const int tile_floats = TA * W * F;
     float* const tile0 = reinterpret_cast<float*>(smem_raw);
     float* const tile1 = tile0 + tile_floats;
-    float* const s_wnew = tile1 + tile_floats;           // [G, A]
+    float* const s_wnew = tile1 + tile_floats;           // [G, A]   w' of the group's envs, indexed by asset-row
+    int* const s_ea = reinterpret_cast<int*>(s_wnew + G * A);   // [G, A]   (env-in-group << 16) | asset per asset-row
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_groups = (p.E + G - 1) / G;
     const size_t row_floats = (size_t)W * F;
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
 #pragma unroll
             for (int j = 0; j < NPL; ++j) {
                 const int a = lane + 32 * j;
-                if (a < A) s_wnew[warp * A + a] = wn[j];
+                if (a < A) { s_wnew[warp * A + a] = wn[j]; if (FAST) s_ea[warp * A + a] = (warp << 16) | a; }
             }
             if (lane == 0) {
                 GroupEnv ge;
@@ -165,75 +167,68 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
         if constexpr (FAST) {
             const float4* __restrict__ tbl = reinterpret_cast<const float4*>(p.feat_am);
             const float* __restrict__ hist_g = p.hist + (size_t)e0 * W * A;
-            RowCursor cf, cw;                       // cursors of this thread's first feature row / its weight row
-            cf.init(warp, A);
-            cw.init(lane, A);
+            // thread-invariant shared-memory offsets of this thread's 8 feature rows / 8 weight columns
+            const int fbase = (warp * W + lane) * 5, fstep = 8 * W * 5;
+            const bool w0 = lane < W, w1 = lane + 32 < W;
+            const int wbase = (lane * W + warp) * 5 + 4;
+            const int nj = min(8, max(0, (W - warp + 7) >> 3));
+            const int WA = W * A;
             TileRegs tr;
-            auto load_tile = [&](int r0) {
-                const int nr = min(32, R - r0);
-                RowCursor c = cf;
+            auto load_tile = [&](int r0, auto partial) {
+                constexpr bool PARTIAL = decltype(partial)::value;
+                const int nr = PARTIAL ? min(32, R - r0) : 32;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int ar = warp + 8 * i;
-                    if (ar < nr) {
-                        const float4* __restrict__ src = tbl + (size_t)c.a * T + s_env[c.el].row0;
-#pragma unroll
-                        for (int cc = 0; cc < 2; ++cc) {
-                            const int w = lane + 32 * cc;
-                            if (w < W) tr.fv[i][cc] = ld_keep4(src + w, pol_keep);
-                        }
+                    if (!PARTIAL || warp + 8 * i < nr) {
+                        const int ea = s_ea[r0 + warp + 8 * i];
+                        const float4* __restrict__ src = tbl + ((ea & 0xffff) * T + s_env[ea >> 16].row0) + lane;
+                        if (w0) tr.fv[i][0] = ld_keep4(src, pol_keep);
+                        if (w1) tr.fv[i][1] = ld_keep4(src + 32, pol_keep);
                     }
-                    c.advance(8, A);
                 }
-                if (lane < nr) {
-                    const GroupEnv ge = s_env[cw.el];
-                    const float* __restrict__ base = hist_g + (size_t)cw.el * W * A + cw.a;
-                    const float fresh = s_wnew[cw.el * A + cw.a];
+                if (!PARTIAL || lane < nr) {
+                    const int ea = s_ea[r0 + lane];
+                    const int el = ea >> 16;
+                    const GroupEnv ge = s_env[el];
+                    const float* __restrict__ base = hist_g + (el * WA + (ea & 0xffff));
+                    const float fresh = s_wnew[r0 + lane];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int w = warp + 8 * j;
-                        const int slot = w - ge.shift;
+                        const int slot = warp + 8 * j - ge.shift;
                         float v = 0.0f;
-                        if (w < W && slot >= 0) v = (slot == ge.fresh_slot) ? fresh : ld_once(base + (size_t)slot * A, pol_once);
+                        if (j < nj && slot >= 0) v = (slot == ge.fresh_slot) ? fresh : ld_once(base + slot * A, pol_once);
                         tr.wv[j] = v;
                     }
                 }
-                cf.advance(32, A);
-                cw.advance(32, A);
             };
-            auto spill_tile = [&](float* __restrict__ tile, int r0) {
-                const int nr = min(32, R - r0);
+            auto spill_tile = [&](float* __restrict__ tile, int r0, auto partial) {
+                constexpr bool PARTIAL = decltype(partial)::value;
+                const int nr = PARTIAL ? min(32, R - r0) : 32;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int ar = warp + 8 * i;
-                    if (ar < nr) {
-#pragma unroll
-                        for (int cc = 0; cc < 2; ++cc) {
-                            const int w = lane + 32 * cc;
-                            if (w < W) {
-                                float* d = tile + (ar * W + w) * 5;
-                                const float4 v = tr.fv[i][cc];
-                                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-                            }
-                        }
+                    if (!PARTIAL || warp + 8 * i < nr) {
+                        float* d = tile + fbase + i * fstep;
+                        if (w0) { const float4 v = tr.fv[i][0]; d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+                        if (w1) { const float4 v = tr.fv[i][1]; d[160] = v.x; d[161] = v.y; d[162] = v.z; d[163] = v.w; }
                     }
                 }
-                if (lane < nr) {
+                if (!PARTIAL || lane < nr) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int w = warp + 8 * j;
-                        if (w < W) tile[(lane * W + w) * 5 + 4] = tr.wv[j];
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        if (j < nj) tile[wbase + 40 * j] = tr.wv[j];
                 }
             };
-            load_tile(0);
+            const int nfull = R >> 5;                      // tiles with all 32 asset-rows
+            if (nfull > 0) load_tile(0, std::false_type{}); else load_tile(0, std::true_type{});
             for (int ti = 0; ti < ntiles; ++ti) {
                 float* const tile = buf ? tile1 : tile0;
                 if (tid == 0) bulk_wait_read<1>();        // the store that last used this buffer has drained
                 __syncthreads();
                 const int r0 = ti * 32;
-                spill_tile(tile, r0);
-                if (ti + 1 < ntiles) load_tile(r0 + 32);  // next tile's loads fly during the barrier + store
+                if (ti < nfull) spill_tile(tile, r0, std::false_type{}); else spill_tile(tile, r0, std::true_type{});
+                if (ti + 1 < ntiles) {                    // next tile's loads fly during the barrier + store
+                    if (ti + 1 < nfull) load_tile(r0 + 32, std::false_type{}); else load_tile(r0 + 32, std::true_type{});
+                }
                 fence_proxy_async_smem();
                 __syncthreads();
                 const int nr = min(32, R - r0);
@@ -458,14 +453,14 @@ static int launch_fused(StepParams& p, float* obs, int npl, cudaStream_t s) {
     while (rows > 1 && rows * row_bytes > 36 * 1024) rows >>= 1;
     p.tile_assets = rows;
     // register-staged, software-pipelined fill for the reference obs shape family
-    const bool fast = (p.F == 5) && (p.W <= 64) && (rows == 32) && g_tune_fast;
+    const bool fast = (p.F == 5) && (p.W <= 64) && (rows == 32) && g_tune_fast && ((size_t)p.A * p.T < (1u << 31)) && p.A < 65536;
     int ctas_per_sm = g_tune_ctas_per_sm > 0 ? g_tune_ctas_per_sm : (npl <= 4 ? 3 : (npl <= 8 ? 2 : 1));
     const int slots = pmrl_sm_count() * ctas_per_sm;
     int G = g_tune_group > 0 ? g_tune_group : kMaxGroup;
     if (G > kMaxGroup) G = kMaxGroup;
     while (G > 1 && (p.E + G - 1) / G < 2 * slots) G >>= 1;     // small batches: more, smaller groups
     p.group_envs = G;
-    const size_t smem = 2 * rows * row_bytes + (size_t)G * p.A * 4;
+    const size_t smem = 2 * rows * row_bytes + (size_t)G * p.A * 8;
     if (smem > 200 * 1024) return pmrl_fail(PMRL_E_SHAPE, "fused step: shared-memory budget exceeded");
     const int n_groups = (p.E + G - 1) / G;
     const int grid = n_groups < slots ? n_groups : slots;

@@ -13,23 +13,24 @@
 
 namespace pmrl {
 
-// One thread per series: the binomial weights are a *sequential* fp32 product (torch.cumprod on the CPU
-// multiplies left to right), so the chain is reproduced bit for bit; N is a few hundred at most.
+// One thread per series: torch.cumprod on the CPU multiplies left to right with a *double* accumulator
+// (ATen acc_type<float>) and rounds every prefix to fp32, so the chain is reproduced bit for bit the same
+// way; N is a few hundred at most.
 __global__ void k_ffd_weights(const double* __restrict__ d, int N, int T, float thres,
                               float* __restrict__ weights, int32_t* __restrict__ widths) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const float factor = (float)(-(d[n] + 1.0));           // zeros(len-1) - (d+1)        (ffd.py:38)
     float* __restrict__ w = weights + (size_t)n * T;
-    float acc = 1.0f;
+    double acc = 1.0;
     int width = 0;
-    w[0] = acc;
-    if (fabsf(acc) > thres) width = 0;
+    w[0] = 1.0f;
     for (int k = 1; k < T; ++k) {
         const float proto = __fadd_rn(__fdiv_rn(factor, (float)k), 1.0f);   // div(factor, k) + 1  (ffd.py:39)
-        acc = __fmul_rn(acc, proto);                                         // cumprod             (ffd.py:40)
-        w[k] = acc;
-        if (fabsf(acc) > thres) width = k;                                   // where(|w|>thres).max() (ffd.py:43)
+        acc *= (double)proto;                                                // cumprod             (ffd.py:40)
+        const float wk = (float)acc;
+        w[k] = wk;
+        if (fabsf(wk) > thres) width = k;                                    // where(|w|>thres).max() (ffd.py:43)
     }
     widths[n] = width;
 }

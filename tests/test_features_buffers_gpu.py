@@ -25,7 +25,7 @@ def test_ffd_matches_reference_golden():
     np.testing.assert_array_equal(widths.cpu().numpy(), g["widths"])                       # integer: bit-exact
     ic = list(g["names"]).index("close")
     wd = int(g["widths"][ic])
-    np.testing.assert_array_equal(w[ic, :wd].flip(0).cpu().numpy(), g["weights_close"])    # sequential fp32 product: bit-exact
+    np.testing.assert_array_equal(w[ic, :wd].flip(0).cpu().numpy(), g["weights_close"])    # sequential product, double accumulator like ATen: bit-exact
     out, widths2, mw = features.ffd_transform(g["x"], g["d"], float(g["thres"]))
     assert mw == int(g["max_width"])
     # conv accumulation order differs from torch's CPU conv1d: fp32 tolerance scaled by the series magnitude (~100)
