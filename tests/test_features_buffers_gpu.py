@@ -196,7 +196,7 @@ def test_pg_reward_matches_reference_autograd(mode):
     pa = torch.from_numpy(g[f"{mode}_pa"]).cuda(); p = torch.from_numpy(g[f"{mode}_p"]).cuda()
     rew, grad = pg_reward(a, pv, pa, p, mode=mode, normalise=True)
     np.testing.assert_allclose(rew.mean().item(), float(g[f"{mode}_r"]), rtol=1e-5, atol=1e-7)
-    np.testing.assert_allclose(grad.cpu().numpy(), g[f"{mode}_grad"], rtol=2e-4, atol=2e-8)
+    np.testing.assert_allclose(grad.cpu().numpy(), g[f"{mode}_grad"].reshape(grad.shape), rtol=2e-4, atol=2e-8)
 
 
 def test_pg_reward_autograd_function():
