@@ -123,6 +123,7 @@ const char* pmrl_last_error(void);
 #define PMRL_TUNE_CTAS_PER_SM 3   /* persistent CTAs per SM */
 #define PMRL_TUNE_FUSED       4   /* 1 (default): fused step+obs kernel; 0: k_env_step followed by k_obs_build */
 #define PMRL_TUNE_FAST_FILL   5   /* 1 (default): register-staged pipelined tile fill when F == 5 && W <= 64 */
+#define PMRL_TUNE_PREFETCH_DEPTH 6 /* 1 (default) or 2 tiles of loads in flight per thread */
 int pmrl_set_tuning(int32_t key, int32_t value);
 
 /* Re-initialise the envs with mask[e] != 0 (mask == NULL → all): V ← initial_cash, ring ← 0 with

@@ -118,7 +118,7 @@ struct RowCursor {        // (env-in-group, asset) of a running asset-row index,
     __device__ __forceinline__ void advance(int d, int A) { a += d; while (a >= A) { a -= A; ++el; } }
 };
 
-template <int NPL, int MINB, bool FAST>
+template <int NPL, int MINB, bool FAST, int DEPTH>
 __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const StepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_stats[kFusedWarps * PMRL_STATS_LEN];
@@ -173,8 +173,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
             const int wbase = (lane * W + warp) * 5 + 4;
             const int nj = min(8, max(0, (W - warp + 7) >> 3));
             const int WA = W * A;
-            TileRegs tr;
-            auto load_tile = [&](int r0, auto partial) {
+            auto load_tile = [&](TileRegs& tr, int r0, auto partial) {
                 constexpr bool PARTIAL = decltype(partial)::value;
                 const int nr = PARTIAL ? min(32, R - r0) : 32;
 #pragma unroll
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
                     }
                 }
             };
-            auto spill_tile = [&](float* __restrict__ tile, int r0, auto partial) {
+            auto spill_tile = [&](const TileRegs& tr, float* __restrict__ tile, int r0, auto partial) {
                 constexpr bool PARTIAL = decltype(partial)::value;
                 const int nr = PARTIAL ? min(32, R - r0) : 32;
 #pragma unroll
@@ -219,16 +218,18 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
                 }
             };
             const int nfull = R >> 5;                      // tiles with all 32 asset-rows
-            if (nfull > 0) load_tile(0, std::false_type{}); else load_tile(0, std::true_type{});
-            for (int ti = 0; ti < ntiles; ++ti) {
+            auto prefetch = [&](TileRegs& tr, int tj) {   // issue the loads of tile tj (if any) into tr
+                if (tj < ntiles) {
+                    if (tj < nfull) load_tile(tr, tj * 32, std::false_type{}); else load_tile(tr, tj * 32, std::true_type{});
+                }
+            };
+            auto emit = [&](TileRegs& tr, int ti) {       // registers → shared tile → TMA store; refill tr DEPTH tiles ahead
                 float* const tile = buf ? tile1 : tile0;
                 if (tid == 0) bulk_wait_read<1>();        // the store that last used this buffer has drained
                 __syncthreads();
                 const int r0 = ti * 32;
-                if (ti < nfull) spill_tile(tile, r0, std::false_type{}); else spill_tile(tile, r0, std::true_type{});
-                if (ti + 1 < ntiles) {                    // next tile's loads fly during the barrier + store
-                    if (ti + 1 < nfull) load_tile(r0 + 32, std::false_type{}); else load_tile(r0 + 32, std::true_type{});
-                }
+                if (ti < nfull) spill_tile(tr, tile, r0, std::false_type{}); else spill_tile(tr, tile, r0, std::true_type{});
+                prefetch(tr, ti + DEPTH);                 // these loads fly during the barrier, the store and DEPTH-1 tiles
                 fence_proxy_async_smem();
                 __syncthreads();
                 const int nr = min(32, R - r0);
@@ -240,6 +241,13 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
                     for (int q = tid; q < n; q += kFusedThreads) gdst[q] = tile[q];
                 }
                 buf ^= 1;
+            };
+            TileRegs trA, trB;
+            prefetch(trA, 0);
+            if (DEPTH == 2) prefetch(trB, 1);
+            for (int ti = 0; ti < ntiles; ti += DEPTH) {
+                emit(trA, ti);
+                if (DEPTH == 2 && ti + 1 < ntiles) emit(trB, ti + 1);
             }
         } else {
         for (int ti = 0; ti < ntiles; ++ti) {
@@ -407,7 +415,7 @@ static int launch_step_s(const StepParams& p, cudaStream_t s) {
 
 
 // Fused Mode-O launch: tile rows, group size and grid from the shape (tunable through pmrl_set_tuning).
-static int g_tune_rows = 0, g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1, g_tune_fast = 1;
+static int g_tune_rows = 0, g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1, g_tune_fast = 1, g_tune_depth = 1;
 
 extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
     switch (key) {
@@ -416,26 +424,35 @@ extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
         case PMRL_TUNE_CTAS_PER_SM: g_tune_ctas_per_sm = value; return 0;
         case PMRL_TUNE_FUSED: g_tune_fused = value; return 0;
         case PMRL_TUNE_FAST_FILL: g_tune_fast = value; return 0;
+        case PMRL_TUNE_PREFETCH_DEPTH: g_tune_depth = value; return 0;
         default: return pmrl_fail(PMRL_E_ARG, "unknown tuning key");
     }
 }
 
-template <int NPL, int MINB, bool FAST>
+template <int NPL, int MINB, bool FAST, int DEPTH = 1>
 static int launch_fused_t(StepParams& p, size_t smem, int grid, cudaStream_t s) {
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs<NPL, MINB, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs<NPL, MINB, FAST, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return pmrl_fail((int)e, "cudaFuncSetAttribute(k_env_step_obs) failed");
         attr_done[dev] = true;
     }
-    k_env_step_obs<NPL, MINB, FAST><<<grid, kFusedThreads, smem, s>>>(p);
+    k_env_step_obs<NPL, MINB, FAST, DEPTH><<<grid, kFusedThreads, smem, s>>>(p);
     return pmrl_check_launch("k_env_step_obs");
 }
 
 template <bool FAST>
 static int launch_fused_npl(StepParams& p, size_t smem, int grid, int npl, cudaStream_t s) {
+    if (FAST && g_tune_depth == 2) {                 // two tiles of loads in flight per thread (128 registers, 2 CTAs/SM)
+        switch (npl) {
+            case 1: return launch_fused_t<1, 2, FAST, 2>(p, smem, grid, s);
+            case 2: return launch_fused_t<2, 2, FAST, 2>(p, smem, grid, s);
+            case 4: return launch_fused_t<4, 2, FAST, 2>(p, smem, grid, s);
+            default: break;
+        }
+    }
     switch (npl) {
         case 1: return launch_fused_t<1, 3, FAST>(p, smem, grid, s);
         case 2: return launch_fused_t<2, 3, FAST>(p, smem, grid, s);
@@ -454,7 +471,7 @@ static int launch_fused(StepParams& p, float* obs, int npl, cudaStream_t s) {
     p.tile_assets = rows;
     // register-staged, software-pipelined fill for the reference obs shape family
     const bool fast = (p.F == 5) && (p.W <= 64) && (rows == 32) && g_tune_fast && ((size_t)p.A * p.T < (1u << 31)) && p.A < 65536;
-    int ctas_per_sm = g_tune_ctas_per_sm > 0 ? g_tune_ctas_per_sm : (npl <= 4 ? 3 : (npl <= 8 ? 2 : 1));
+    int ctas_per_sm = g_tune_ctas_per_sm > 0 ? g_tune_ctas_per_sm : (npl <= 4 ? (fast && g_tune_depth == 2 ? 2 : 3) : (npl <= 8 ? 2 : 1));
     const int slots = pmrl_sm_count() * ctas_per_sm;
     int G = g_tune_group > 0 ? g_tune_group : kMaxGroup;
     if (G > kMaxGroup) G = kMaxGroup;
