@@ -15,6 +15,7 @@
 #include "env_step.cuh"
 #include "obs_tile.cuh"
 #include "host_util.h"
+#include "env_launch.h"
 
 namespace pmrl {
 
@@ -25,17 +26,33 @@ constexpr int kObsThreads = 256;
 // ------------------------------------------------------------------------------------------------
 // Mode S: state-only step.
 // ------------------------------------------------------------------------------------------------
-template <int NPL>
+template <int NPL, bool HASC, bool PIPE>
 __global__ void __launch_bounds__(kStepThreads) k_env_step(const StepParams p) {
     __shared__ double s_stats[kStepWarps * PMRL_STATS_LEN];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kStepWarps + warp;
     const int nw = gridDim.x * kStepWarps;
     if (p.stats) stats_init_block(s_stats, kStepWarps);
-    for (int e = gw; e < p.E; e += nw) {
-        float wn[NPL];
-        StepOut so;
-        env_step_warp<NPL>(p, e, lane, wn, so, s_stats + warp * PMRL_STATS_LEN);
+    double* const acc = s_stats + warp * PMRL_STATS_LEN;
+    StepOut so;
+    if constexpr (PIPE) {
+        // three envs of this warp in flight: scalars of e+2nw, vectors of e+nw, arithmetic of e
+        EnvScalars s0, s1, s2;
+        EnvVectors<NPL, HASC> v0, v1;
+        int e = gw;
+        if (e < p.E) { env_load_scalars(p, e, s0); env_load_vectors<NPL, HASC>(p, e, lane, s0, v0); }
+        if (e + nw < p.E) env_load_scalars(p, e + nw, s1);
+        for (; e < p.E; e += nw) {
+            if (e + 2 * nw < p.E) env_load_scalars(p, e + 2 * nw, s2);
+            if (e + nw < p.E) env_load_vectors<NPL, HASC>(p, e + nw, lane, s1, v1);
+            env_compute_store<NPL, HASC>(p, e, lane, s0, v0, so, acc);
+            s0 = s1; s1 = s2; v0 = v1;
+        }
+    } else {
+        for (int e = gw; e < p.E; e += nw) {
+            EnvVectors<NPL, HASC> v;
+            env_step_warp<NPL, HASC>(p, e, lane, v, so, acc);
+        }
     }
     if (p.stats) stats_flush_block(p.stats, s_stats, kStepWarps);
 }
@@ -118,7 +135,7 @@ struct RowCursor {        // (env-in-group, asset) of a running asset-row index,
     __device__ __forceinline__ void advance(int d, int A) { a += d; while (a >= A) { a -= A; ++el; } }
 };
 
-template <int NPL, int MINB, bool FAST, int DEPTH>
+template <int NPL, bool HASC, int MINB, bool FAST, int DEPTH>
 __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const StepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_stats[kFusedWarps * PMRL_STATS_LEN];
@@ -141,13 +158,13 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
         // ---------------- phase 1: one warp per env ----------------
         if (warp < ne) {
             const int e = e0 + warp;
-            float wn[NPL];
+            EnvVectors<NPL, HASC> ev;
             StepOut so;
-            env_step_warp<NPL>(p, e, lane, wn, so, s_stats + warp * PMRL_STATS_LEN);
+            env_step_warp<NPL, HASC>(p, e, lane, ev, so, s_stats + warp * PMRL_STATS_LEN);
 #pragma unroll
             for (int j = 0; j < NPL; ++j) {
                 const int a = lane + 32 * j;
-                if (a < A) { s_wnew[warp * A + a] = wn[j]; if (FAST) s_ea[warp * A + a] = (warp << 16) | a; }
+                if (a < A) { s_wnew[warp * A + a] = ev.a[j]; if (FAST) s_ea[warp * A + a] = (warp << 16) | a; }
             }
             if (lane == 0) {
                 GroupEnv ge;
@@ -181,8 +198,8 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
                     if (!PARTIAL || warp + 8 * i < nr) {
                         const int ea = s_ea[r0 + warp + 8 * i];
                         const float4* __restrict__ src = tbl + ((ea & 0xffff) * T + s_env[ea >> 16].row0) + lane;
-                        if (w0) tr.fv[i][0] = ld_keep4(src, pol_keep);
-                        if (w1) tr.fv[i][1] = ld_keep4(src + 32, pol_keep);
+                        if (w0 && !(p.debug_skip & 2)) tr.fv[i][0] = ld_keep4(src, pol_keep);
+                        if (w1 && !(p.debug_skip & 2)) tr.fv[i][1] = ld_keep4(src + 32, pol_keep);
                     }
                 }
                 if (!PARTIAL || lane < nr) {
@@ -195,7 +212,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
                     for (int j = 0; j < 8; ++j) {
                         const int slot = warp + 8 * j - ge.shift;
                         float v = 0.0f;
-                        if (j < nj && slot >= 0) v = (slot == ge.fresh_slot) ? fresh : ld_once(base + slot * A, pol_once);
+                        if (j < nj && slot >= 0 && !(p.debug_skip & 1)) v = (slot == ge.fresh_slot) ? fresh : ld_once(base + slot * A, pol_once);
                         tr.wv[j] = v;
                     }
                 }
@@ -235,7 +252,8 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
                 const int nr = min(32, R - r0);
                 float* const gdst = obs_grp + (size_t)r0 * row_floats;
                 const int n = nr * W * 5;
-                if (((((uintptr_t)gdst) | ((size_t)n * 4)) & 15) == 0) {
+                if (p.debug_skip & 4) {
+                } else if (((((uintptr_t)gdst) | ((size_t)n * 4)) & 15) == 0) {
                     if (tid == 0) { bulk_store_s2g(gdst, tile, (uint32_t)n * 4u, pol_once); bulk_commit(); }
                 } else {
                     for (int q = tid; q < n; q += kFusedThreads) gdst[q] = tile[q];
@@ -405,17 +423,29 @@ static int launch_obs(StepParams& p, float* obs, int obs_mode, cudaStream_t s) {
     return pmrl_check_launch("k_obs_build");
 }
 
-template <int NPL>
+template <int NPL, bool HASC>
 static int launch_step_s(const StepParams& p, cudaStream_t s) {
+    constexpr bool PIPE = (NPL <= 4);                 // 3-stage software pipeline while the registers allow it
     const int want = (p.E + kStepWarps - 1) / kStepWarps;
     const int cap = pmrl_sm_count() * 8;
-    k_env_step<NPL><<<want < cap ? want : cap, kStepThreads, 0, s>>>(p);
+    k_env_step<NPL, HASC, PIPE><<<want < cap ? want : cap, kStepThreads, 0, s>>>(p);
     return pmrl_check_launch("k_env_step");
 }
 
+template <bool HASC>
+static int launch_step_npl(const StepParams& p, int npl, cudaStream_t s) {
+    switch (npl) {
+        case 1: return launch_step_s<1, HASC>(p, s);
+        case 2: return launch_step_s<2, HASC>(p, s);
+        case 4: return launch_step_s<4, HASC>(p, s);
+        case 8: return launch_step_s<8, HASC>(p, s);
+        case 16: return launch_step_s<16, HASC>(p, s);
+        default: return launch_step_s<32, HASC>(p, s);
+    }
+}
 
 // Fused Mode-O launch: tile rows, group size and grid from the shape (tunable through pmrl_set_tuning).
-static int g_tune_rows = 0, g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1, g_tune_fast = 1, g_tune_depth = 1;
+static int g_tune_rows = 0, g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1, g_tune_fast = 1, g_tune_depth = 1, g_tune_skip = 0, g_tune_tma = 0, g_tune_stages = 0;
 
 extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
     switch (key) {
@@ -425,46 +455,54 @@ extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
         case PMRL_TUNE_FUSED: g_tune_fused = value; return 0;
         case PMRL_TUNE_FAST_FILL: g_tune_fast = value; return 0;
         case PMRL_TUNE_PREFETCH_DEPTH: g_tune_depth = value; return 0;
+        case PMRL_TUNE_DEBUG_SKIP: g_tune_skip = value; return 0;
+        case PMRL_TUNE_TMA_PIPELINE: g_tune_tma = value; return 0;
+        case PMRL_TUNE_TMA_STAGES: g_tune_stages = value; return 0;
         default: return pmrl_fail(PMRL_E_ARG, "unknown tuning key");
     }
 }
 
-template <int NPL, int MINB, bool FAST, int DEPTH = 1>
+template <int NPL, bool HASC, int MINB, bool FAST, int DEPTH>
 static int launch_fused_t(StepParams& p, size_t smem, int grid, cudaStream_t s) {
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs<NPL, MINB, FAST, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs<NPL, HASC, MINB, FAST, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return pmrl_fail((int)e, "cudaFuncSetAttribute(k_env_step_obs) failed");
         attr_done[dev] = true;
     }
-    k_env_step_obs<NPL, MINB, FAST, DEPTH><<<grid, kFusedThreads, smem, s>>>(p);
+    k_env_step_obs<NPL, HASC, MINB, FAST, DEPTH><<<grid, kFusedThreads, smem, s>>>(p);
     return pmrl_check_launch("k_env_step_obs");
 }
 
-template <bool FAST>
+template <bool HASC, bool FAST>
 static int launch_fused_npl(StepParams& p, size_t smem, int grid, int npl, cudaStream_t s) {
     if (FAST && g_tune_depth == 2) {                 // two tiles of loads in flight per thread (128 registers, 2 CTAs/SM)
         switch (npl) {
-            case 1: return launch_fused_t<1, 2, FAST, 2>(p, smem, grid, s);
-            case 2: return launch_fused_t<2, 2, FAST, 2>(p, smem, grid, s);
-            case 4: return launch_fused_t<4, 2, FAST, 2>(p, smem, grid, s);
+            case 1: return launch_fused_t<1, HASC, 2, FAST, 2>(p, smem, grid, s);
+            case 2: return launch_fused_t<2, HASC, 2, FAST, 2>(p, smem, grid, s);
+            case 4: return launch_fused_t<4, HASC, 2, FAST, 2>(p, smem, grid, s);
             default: break;
         }
     }
     switch (npl) {
-        case 1: return launch_fused_t<1, 3, FAST>(p, smem, grid, s);
-        case 2: return launch_fused_t<2, 3, FAST>(p, smem, grid, s);
-        case 4: return launch_fused_t<4, 3, FAST>(p, smem, grid, s);
-        case 8: return launch_fused_t<8, 2, FAST>(p, smem, grid, s);
-        case 16: return launch_fused_t<16, 1, FAST>(p, smem, grid, s);
-        default: return launch_fused_t<32, 1, FAST>(p, smem, grid, s);
+        case 1: return launch_fused_t<1, HASC, 3, FAST, 1>(p, smem, grid, s);
+        case 2: return launch_fused_t<2, HASC, 3, FAST, 1>(p, smem, grid, s);
+        case 4: return launch_fused_t<4, HASC, 3, FAST, 1>(p, smem, grid, s);
+        case 8: return launch_fused_t<8, HASC, 2, FAST, 1>(p, smem, grid, s);
+        case 16: return launch_fused_t<16, HASC, 1, FAST, 1>(p, smem, grid, s);
+        default: return launch_fused_t<32, HASC, 1, FAST, 1>(p, smem, grid, s);
     }
 }
 
 static int launch_fused(StepParams& p, float* obs, int npl, cudaStream_t s) {
     p.obs = obs; p.obs_mode = PMRL_OBS_FULL;
+    p.debug_skip = g_tune_skip;
+    if (g_tune_tma && g_tune_fast) {                  // warp-specialised TMA pipeline (env_step_tma.cu)
+        const int rc = pmrl_launch_step_obs_tma(p, npl, g_tune_stages, g_tune_group, s);
+        if (rc != -100) return rc;                    // -100: shape not covered by that variant → fall through
+    }
     const size_t row_bytes = (size_t)p.W * p.F * 4;
     int rows = g_tune_rows > 0 ? g_tune_rows : 32;
     while (rows > 1 && rows * row_bytes > 36 * 1024) rows >>= 1;
@@ -481,7 +519,9 @@ static int launch_fused(StepParams& p, float* obs, int npl, cudaStream_t s) {
     if (smem > 200 * 1024) return pmrl_fail(PMRL_E_SHAPE, "fused step: shared-memory budget exceeded");
     const int n_groups = (p.E + G - 1) / G;
     const int grid = n_groups < slots ? n_groups : slots;
-    return fast ? launch_fused_npl<true>(p, smem, grid, npl, s) : launch_fused_npl<false>(p, smem, grid, npl, s);
+    const bool hasc = p.commission > 0.0f;
+    if (fast) return hasc ? launch_fused_npl<true, true>(p, smem, grid, npl, s) : launch_fused_npl<false, true>(p, smem, grid, npl, s);
+    return hasc ? launch_fused_npl<true, false>(p, smem, grid, npl, s) : launch_fused_npl<false, false>(p, smem, grid, npl, s);
 }
 
 extern "C" int pmrl_env_reset(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
@@ -535,15 +575,7 @@ extern "C" int pmrl_env_step(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const
     if (p.E == 0) return 0;
     if (obs_mode == PMRL_OBS_FULL && g_tune_fused && (size_t)p.W * p.F * 4 <= 36 * 1024)
         return launch_fused(p, obs, npl, s);
-    int rc = 0;
-    switch (npl) {
-        case 1: rc = launch_step_s<1>(p, s); break;
-        case 2: rc = launch_step_s<2>(p, s); break;
-        case 4: rc = launch_step_s<4>(p, s); break;
-        case 8: rc = launch_step_s<8>(p, s); break;
-        case 16: rc = launch_step_s<16>(p, s); break;
-        default: rc = launch_step_s<32>(p, s); break;
-    }
+    int rc = p.commission > 0.0f ? launch_step_npl<true>(p, npl, s) : launch_step_npl<false>(p, npl, s);
     if (rc) return rc;
     if (obs_mode != PMRL_OBS_NONE) return launch_obs(p, obs, obs_mode, s);
     return 0;

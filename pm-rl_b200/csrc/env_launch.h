@@ -1,0 +1,8 @@
+// env_launch.h — internal: launchers shared between the env translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include "pmrl_device.cuh"
+
+// Warp-specialised TMA pipeline variant of the fused step+obs kernel (env_step_tma.cu).
+// Returns -100 if the shape is not supported by this variant (caller falls back).
+int pmrl_launch_step_obs_tma(pmrl::StepParams& p, int npl, int stages, int group, cudaStream_t s);

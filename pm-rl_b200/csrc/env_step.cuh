@@ -7,6 +7,13 @@
 //   y_t = close_t / close_{t-1}   data/instrument.py:79
 // keeping the reference association of every fp32 operation (no FMA contraction, IEEE div,
 // expf/logf without fast-math) so values stay within 1e-5 relative over 1,000 compounding steps.
+//
+// The transition is split into three stages so that the state-only kernel can software-pipeline them
+// across consecutive envs of a warp (scalars of env n+2, vectors of env n+1 and the arithmetic of env n
+// are in flight together):
+//   env_load_scalars   V, ring pointer, is_full, local step, episode offset
+//   env_load_vectors   raw action, the two close rows (or external y), previous weights (commission only)
+//   env_compute_store  everything else
 #pragma once
 #include "pmrl_device.cuh"
 
@@ -30,28 +37,86 @@ struct StepOut {       // warp-uniform result of one env transition
     int done;
 };
 
+struct EnvScalars { float V; int i, full, k, t0e; };
+
+template <int NPL, bool HASC>
+struct EnvVectors {
+    float a[NPL];                   // raw action → weights → holdings → w'  (updated in place)
+    float c1[NPL];                  // close_t (or external y)
+    float c0[NPL];                  // close_{t-1}
+    float wl[HASC ? NPL : 1];       // previous post-drift weights (only read when commission > 0)
+};
+
 // Zero the ring of env e and set the all-cash row (weight_buffer.py:46-50).
 __device__ __forceinline__ void ring_reset_warp(float* __restrict__ hist_e, int W, int A, int lane) {
     const int n = W * A;
     for (int i = lane; i < n; i += 32) hist_e[i] = (i == 0) ? 1.0f : 0.0f;
 }
 
-template <int NPL>
-__device__ __forceinline__ void env_step_warp(const StepParams& p, int e, int lane,
-                                              float (&wn)[NPL], StepOut& out, double* __restrict__ acc /* smem [10] of this warp */) {
+__device__ __forceinline__ void env_load_scalars(const StepParams& p, int e, EnvScalars& s) {
+    s.V = p.value[e];
+    s.i = p.idx[e];
+    s.full = p.is_full[e];
+    s.k = p.t[e];
+    s.t0e = p.t0 ? p.t0[e] : 0;
+}
+
+__device__ __forceinline__ bool env_needs_reset(const StepParams& p, const EnvScalars& s) {
+    return p.episode_len > 0 && s.k >= p.episode_len;           // train/on_policy.py:60-61
+}
+
+template <int NPL, bool HASC>
+__device__ __forceinline__ void env_load_vectors(const StepParams& p, int e, int lane, const EnvScalars& s,
+                                                 EnvVectors<NPL, HASC>& v) {
+    if (env_needs_reset(p, s)) return;                           // nothing is read on the auto-reset call
     const int A = p.A, W = p.W;
     const size_t eA = (size_t)e * A;
+    const uint64_t pol_once = l2_policy_evict_first();
+    if (p.y_ext) {
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int a = lane + 32 * j;
+            v.c1[j] = (a < A) ? ld_once(p.y_ext + eA + a, pol_once) : 0.0f;
+            v.c0[j] = 1.0f;
+        }
+    } else {
+        const uint64_t pol_keep = l2_policy_evict_last();
+        const size_t row = (size_t)(s.t0e + s.k + W);            // row t0 + k_new + W - 1: last row of the new window
+        const float* __restrict__ r1 = p.close_tm + row * A;
+        const float* __restrict__ r0 = r1 - A;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int a = lane + 32 * j;
+            v.c1[j] = (a < A) ? ld_keep(r1 + a, pol_keep) : 0.0f;
+            v.c0[j] = (a < A) ? ld_keep(r0 + a, pol_keep) : 1.0f;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        const int a = lane + 32 * j;
+        v.a[j] = (a < A) ? ld_once(p.actions + eA + a, pol_once) : 0.0f;
+    }
+    if (HASC) {
+        const int last_slot = (s.i - 1 + W) % W;                 // weight_buffer.py:30
+        const float* __restrict__ wrow = p.hist + ((size_t)e * W + last_slot) * A;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int a = lane + 32 * j;
+            v.wl[j] = (a < A) ? wrow[a] : 0.0f;
+        }
+    }
+}
 
-    // ---- state ----
-    float V = p.value[e];
-    int i = p.idx[e];
-    int full = p.is_full[e];
-    int k = p.t[e];
-    const int t0e = p.t0 ? p.t0[e] : 0;
+// On return v.a[] holds w' (the post-drift weights, lane-strided: asset a = lane + 32*j).
+template <int NPL, bool HASC>
+__device__ __forceinline__ void env_compute_store(const StepParams& p, int e, int lane, const EnvScalars& sc,
+                                                  EnvVectors<NPL, HASC>& v, StepOut& out,
+                                                  double* __restrict__ acc /* smem [10] of this warp */) {
+    const int A = p.A, W = p.W;
     float* __restrict__ hist_e = p.hist + (size_t)e * W * A;
 
     // ---- auto-reset instead of a step (train/on_policy.py:60-61) ----
-    if (p.episode_len > 0 && k >= p.episode_len) {
+    if (env_needs_reset(p, sc)) {
         ring_reset_warp(hist_e, W, A, lane);
         if (lane == 0) {
             p.value[e] = p.initial_cash;
@@ -61,48 +126,22 @@ __device__ __forceinline__ void env_step_warp(const StepParams& p, int e, int la
             if (p.ep_return) p.ep_return[e] = 0.0f;
         }
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) wn[j] = (lane + 32 * j == 0) ? 1.0f : 0.0f;
+        for (int j = 0; j < NPL; ++j) v.a[j] = (lane + 32 * j == 0) ? 1.0f : 0.0f;
         out.idx_new = 1; out.slot_written = -1; out.is_full = 0; out.k = 0; out.did_reset = 1;
         out.V = p.initial_cash; out.reward = 0.0f; out.done = 0;
         return;
     }
 
-    const int k_new = k + 1;
-
-    // ---- inputs: raw action, price relative, previous weights (all loads issued before use) ----
-    float a_raw[NPL], y[NPL], wl[NPL];
-    const bool need_wl = p.commission > 0.0f;
-    const int last_slot = (i - 1 + W) % W;                       // weight_buffer.py:30
-    if (p.y_ext) {
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-            const int a = lane + 32 * j;
-            y[j] = (a < A) ? ld_stream(p.y_ext + eA + a) : 0.0f;
-        }
-    } else {
-        const uint64_t pol_keep = l2_policy_evict_last();
-        const size_t row = (size_t)(t0e + k_new + W - 1);        // y of the window's last row
-        const float* __restrict__ c1 = p.close_tm + row * A;
-        const float* __restrict__ c0 = c1 - A;
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-            const int a = lane + 32 * j;
-            y[j] = (a < A) ? __fdiv_rn(ld_keep(c1 + a, pol_keep), ld_keep(c0 + a, pol_keep)) : 0.0f;   // instrument.py:79
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-        const int a = lane + 32 * j;
-        a_raw[j] = (a < A) ? ld_stream(p.actions + eA + a) : 0.0f;
-        wl[j] = (need_wl && a < A) ? hist_e[(size_t)last_slot * A + a] : 0.0f;
-    }
+    float V = sc.V;
+    const int i = sc.i;
+    int full = sc.full;
+    const int k_new = sc.k + 1;
 
     // ---- normalise (trading_env.py:58-60; quirks Q1-Q3) ----
     float s = 0.0f, mn = INFINITY;
 #pragma unroll
     for (int j = 0; j < NPL; ++j) {
-        const int a = lane + 32 * j;
-        if (a < A) { s = __fadd_rn(s, a_raw[j]); mn = nanmin(mn, a_raw[j]); }
+        if (lane + 32 * j < A) { s = __fadd_rn(s, v.a[j]); mn = nanmin(mn, v.a[j]); }
     }
     s = warp_sum(s);
     mn = warp_min_nan(mn);
@@ -110,36 +149,31 @@ __device__ __forceinline__ void env_step_warp(const StepParams& p, int e, int la
     const bool not_close = !isclose_one(s);
     const bool has_neg = mn < 0.0f;
     const bool normalise = strict ? (not_close && has_neg) : (not_close || has_neg);
-    float w[NPL];
     if (normalise) {
         float mx = 0.0f;
         if (!strict) {                                           // stabilised softmax (agent/pg/pg.py:53)
             mx = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < NPL; ++j) if (lane + 32 * j < A) mx = fmaxf(mx, a_raw[j]);
+            for (int j = 0; j < NPL; ++j) if (lane + 32 * j < A) mx = fmaxf(mx, v.a[j]);
             mx = warp_max(mx);
         }
         float se = 0.0f;
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
-            const int a = lane + 32 * j;
-            w[j] = (a < A) ? expf(__fsub_rn(a_raw[j], mx)) : 0.0f;
-            se = __fadd_rn(se, w[j]);
+            v.a[j] = (lane + 32 * j < A) ? expf(__fsub_rn(v.a[j], mx)) : 0.0f;
+            se = __fadd_rn(se, v.a[j]);
         }
         se = warp_sum(se);
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) w[j] = __fdiv_rn(w[j], se);
-    } else {
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) w[j] = a_raw[j];
+        for (int j = 0; j < NPL; ++j) v.a[j] = __fdiv_rn(v.a[j], se);
     }
 
     // ---- transaction remainder factor mu (trading_env.py:67-75; upstream PGPortfolio relu form) ----
     const float V_prev = V;
-    if (need_wl) {
+    if (HASC) {
         const float c = p.commission;
-        const float w0 = __shfl_sync(PMRL_FULL_MASK, w[0], 0);
-        const float wl0 = __shfl_sync(PMRL_FULL_MASK, wl[0], 0);
+        const float w0 = __shfl_sync(PMRL_FULL_MASK, v.a[0], 0);
+        const float wl0 = __shfl_sync(PMRL_FULL_MASK, v.wl[0], 0);
         const float denom = __fsub_rn(1.0f, __fmul_rn(c, w0));
         const float cw = __fmul_rn(c, wl0);
         float mu_last = 1.0f, mu = p.mu0;
@@ -150,7 +184,7 @@ __device__ __forceinline__ void env_step_warp(const StepParams& p, int e, int la
 #pragma unroll
             for (int j = 0; j < NPL; ++j) {
                 const int a = lane + 32 * j;
-                if (a >= 1 && a < A) part = __fadd_rn(part, fmaxf(__fsub_rn(wl[j], __fmul_rn(mu, w[j])), 0.0f));
+                if (a >= 1 && a < A) part = __fadd_rn(part, fmaxf(__fsub_rn(v.wl[j], __fmul_rn(mu, v.a[j])), 0.0f));
             }
             part = warp_sum(part);
             const float numer = __fsub_rn(__fsub_rn(1.0f, cw), __fmul_rn(p.c2, part));
@@ -160,24 +194,24 @@ __device__ __forceinline__ void env_step_warp(const StepParams& p, int e, int la
         V = __fmul_rn(mu, V);                                    // trading_env.py:75
     }
 
-    // ---- value, drift, return (trading_env.py:78-90) ----
-    float port[NPL], part = 0.0f;
+    // ---- value, drift, return (trading_env.py:78-90); y = close_t / close_{t-1} (instrument.py:79) ----
+    float part = 0.0f;
 #pragma unroll
     for (int j = 0; j < NPL; ++j) {
-        const int a = lane + 32 * j;
-        port[j] = (a < A) ? __fmul_rn(V, __fmul_rn(w[j], y[j])) : 0.0f;
-        part = __fadd_rn(part, port[j]);
+        const float y = __fdiv_rn(v.c1[j], v.c0[j]);
+        v.a[j] = (lane + 32 * j < A) ? __fmul_rn(V, __fmul_rn(v.a[j], y)) : 0.0f;
+        part = __fadd_rn(part, v.a[j]);
     }
     const float Vn = warp_sum(part);
 #pragma unroll
-    for (int j = 0; j < NPL; ++j) wn[j] = __fdiv_rn(port[j], Vn);
+    for (int j = 0; j < NPL; ++j) v.a[j] = __fdiv_rn(v.a[j], Vn);
     const float ret = __fdiv_rn(Vn, V);
 
     // ---- ring write (weight_buffer.py:21-26) ----
 #pragma unroll
     for (int j = 0; j < NPL; ++j) {
         const int a = lane + 32 * j;
-        if (a < A) hist_e[(size_t)i * A + a] = wn[j];
+        if (a < A) hist_e[(size_t)i * A + a] = v.a[j];
     }
     const int i_new = (i + 1 == W) ? 0 : i + 1;
     if (i_new == 0) full = 1;
@@ -224,6 +258,16 @@ __device__ __forceinline__ void env_step_warp(const StepParams& p, int e, int la
     }
     out.idx_new = i_new; out.slot_written = i; out.is_full = full; out.k = k_new; out.did_reset = 0;
     out.V = Vn; out.reward = r; out.done = dn;
+}
+
+// The three stages back to back (fused kernel phase 1).
+template <int NPL, bool HASC>
+__device__ __forceinline__ void env_step_warp(const StepParams& p, int e, int lane, EnvVectors<NPL, HASC>& v,
+                                              StepOut& out, double* __restrict__ acc) {
+    EnvScalars sc;
+    env_load_scalars(p, e, sc);
+    env_load_vectors<NPL, HASC>(p, e, lane, sc, v);
+    env_compute_store<NPL, HASC>(p, e, lane, sc, v, out, acc);
 }
 
 // Block-level flush of the per-warp partials: thread q < 10 folds column q over the warps → 10 atomics per CTA.

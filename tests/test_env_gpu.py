@@ -94,13 +94,18 @@ def test_cuda_replays_reference_rollout(name):
 def tuning():
     from pmrl_b200 import _lib
     yield _lib
-    for k in (_lib.TUNE_TILE_ROWS, _lib.TUNE_GROUP_ENVS, _lib.TUNE_CTAS_PER_SM):
+    for k in (_lib.TUNE_TILE_ROWS, _lib.TUNE_GROUP_ENVS, _lib.TUNE_CTAS_PER_SM, _lib.TUNE_TMA_STAGES):
         _lib.set_tuning(k, 0)
     _lib.set_tuning(_lib.TUNE_FUSED, 1)
+    _lib.set_tuning(_lib.TUNE_TMA_PIPELINE, DEFAULT_TMA)
+    _lib.set_tuning(_lib.TUNE_PREFETCH_DEPTH, 1)
 
 
-# (fused, tile_rows, group_envs): the fused step+obs kernel in several launch shapes, and the two-kernel path
-VARIANTS = [(1, 0, 0), (1, 8, 3), (1, 32, 1), (0, 0, 0)]
+DEFAULT_TMA = 0
+# (fused, tile_rows, group_envs, tma, stages/depth): the fused step+obs kernel in several launch shapes (register-staged
+# fill, two-tile prefetch, warp-specialised TMA pipeline with 2..6 stages) and the two-kernel path
+VARIANTS = [(1, 0, 0, 0, 1), (1, 8, 3, 0, 1), (1, 32, 1, 0, 1), (1, 0, 0, 0, 2), (0, 0, 0, 0, 1),
+            (1, 0, 0, 1, 4), (1, 0, 2, 1, 2), (1, 0, 8, 1, 6)]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -108,10 +113,15 @@ VARIANTS = [(1, 0, 0), (1, 8, 3), (1, 32, 1), (0, 0, 0)]
                                      (33, 9, 6, 48), (130, 16, 2, 40), (1, 4, 5, 9), (3, 300, 5, 5)])
 def test_table_driven_step_and_obs_vs_oracle(A, W, F, E, variant, tuning):
     """Batched, table-driven: window gather, y from the close plane, ring wrap, done and auto-reset."""
-    fused, rows, group = variant
+    fused, rows, group, tma, depth = variant
     tuning.set_tuning(tuning.TUNE_FUSED, fused)
     tuning.set_tuning(tuning.TUNE_TILE_ROWS, rows)
     tuning.set_tuning(tuning.TUNE_GROUP_ENVS, group)
+    tuning.set_tuning(tuning.TUNE_TMA_PIPELINE, tma)
+    if tma:
+        tuning.set_tuning(tuning.TUNE_TMA_STAGES, depth)
+    else:
+        tuning.set_tuning(tuning.TUNE_PREFETCH_DEPTH, depth)
     L = W + 7
     gpu, ora = make_pair(E, A, W, F, episode_len=L)
     g = torch.Generator().manual_seed(99)
