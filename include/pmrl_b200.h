@@ -122,11 +122,9 @@ const char* pmrl_last_error(void);
 #define PMRL_TUNE_GROUP_ENVS  2   /* envs a CTA advances together (1..8) */
 #define PMRL_TUNE_CTAS_PER_SM 3   /* persistent CTAs per SM */
 #define PMRL_TUNE_FUSED       4   /* 1 (default): fused step+obs kernel; 0: k_env_step followed by k_obs_build */
-#define PMRL_TUNE_FAST_FILL   5   /* 1 (default): register-staged pipelined tile fill when F == 5 && W <= 64 */
-#define PMRL_TUNE_PREFETCH_DEPTH 6 /* 1 (default) or 2 tiles of loads in flight per thread */
+#define PMRL_TUNE_FAST_FILL   5   /* 1 (default): specialised kernels (register-staged fill / TMA pipeline) when F == 5 && W <= 64 */
 #define PMRL_TUNE_TMA_PIPELINE 8  /* 1: warp-specialised TMA-load pipeline variant of the fused kernel (F == 5, W <= 64, A <= 512) */
 #define PMRL_TUNE_TMA_STAGES  9   /* staging buffers of that variant (2..6) */
-#define PMRL_TUNE_DEBUG_SKIP  7   /* bandwidth attribution ONLY (results become wrong): bit0 skip ring loads, bit1 skip table loads, bit2 skip obs stores */
 int pmrl_set_tuning(int32_t key, int32_t value);
 
 /* Re-initialise the envs with mask[e] != 0 (mask == NULL → all): V ← initial_cash, ring ← 0 with

@@ -9,7 +9,6 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
-#include <type_traits>
 #include "pmrl_b200.h"
 #include "pmrl_device.cuh"
 #include "env_step.cuh"
@@ -119,23 +118,7 @@ constexpr int kMaxGroup = kFusedWarps;
 
 struct GroupEnv { int row0, shift, fresh_slot, pad; };   // per env of the group (phase 1 → phase 2)
 
-// Register-staged tile loader of the fast path (F == 5, W <= 64, 32 asset-rows per tile).  A thread owns
-//   features: asset-rows ar = warp + 8*i (i < 4), window rows w = lane + 32*c (c < 2)  → 8 float4 loads
-//   weights : asset-row  ar = lane,               columns     w = warp + 8*j  (j < 8)  → 8 scalar loads
-// All 16 loads of a tile are issued back to back (memory-level parallelism), and the loads of tile i+1 are
-// issued before tile i is handed to the TMA store, so the L2/DRAM latency overlaps the barriers and the store.
-struct TileRegs {
-    float4 fv[4][2];
-    float wv[8];
-};
-
-struct RowCursor {        // (env-in-group, asset) of a running asset-row index, advanced without divisions
-    int el, a;
-    __device__ __forceinline__ void init(int gar, int A) { el = gar / A; a = gar - el * A; }
-    __device__ __forceinline__ void advance(int d, int A) { a += d; while (a >= A) { a -= A; ++el; } }
-};
-
-template <int NPL, bool HASC, int MINB, bool FAST, int DEPTH>
+template <int NPL, bool HASC, int MINB>
 __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const StepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_stats[kFusedWarps * PMRL_STATS_LEN];
@@ -145,12 +128,11 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
     float* const tile0 = reinterpret_cast<float*>(smem_raw);
     float* const tile1 = tile0 + tile_floats;
     float* const s_wnew = tile1 + tile_floats;           // [G, A]   w' of the group's envs, indexed by asset-row
-    int* const s_ea = reinterpret_cast<int*>(s_wnew + G * A);   // [G, A]   (env-in-group << 16) | asset per asset-row
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_groups = (p.E + G - 1) / G;
     const size_t row_floats = (size_t)W * F;
     if (p.stats) stats_init_block(s_stats, kFusedWarps);
-    const uint64_t pol_keep = l2_policy_evict_last(), pol_once = l2_policy_evict_first();
+    const uint64_t pol_keep = kPolicyEvictLast, pol_once = kPolicyEvictFirst;
     int buf = 0;
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int e0 = grp * G;
@@ -164,7 +146,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
 #pragma unroll
             for (int j = 0; j < NPL; ++j) {
                 const int a = lane + 32 * j;
-                if (a < A) { s_wnew[warp * A + a] = ev.a[j]; if (FAST) s_ea[warp * A + a] = (warp << 16) | a; }
+                if (a < A) s_wnew[warp * A + a] = ev.a[j];
             }
             if (lane == 0) {
                 GroupEnv ge;
@@ -181,93 +163,6 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
         const int ntiles = (R + TA - 1) / TA;
         float* const obs_grp = p.obs + (size_t)e0 * A * row_floats;
 
-        if constexpr (FAST) {
-            const float4* __restrict__ tbl = reinterpret_cast<const float4*>(p.feat_am);
-            const float* __restrict__ hist_g = p.hist + (size_t)e0 * W * A;
-            // thread-invariant shared-memory offsets of this thread's 8 feature rows / 8 weight columns
-            const int fbase = (warp * W + lane) * 5, fstep = 8 * W * 5;
-            const bool w0 = lane < W, w1 = lane + 32 < W;
-            const int wbase = (lane * W + warp) * 5 + 4;
-            const int nj = min(8, max(0, (W - warp + 7) >> 3));
-            const int WA = W * A;
-            auto load_tile = [&](TileRegs& tr, int r0, auto partial) {
-                constexpr bool PARTIAL = decltype(partial)::value;
-                const int nr = PARTIAL ? min(32, R - r0) : 32;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (!PARTIAL || warp + 8 * i < nr) {
-                        const int ea = s_ea[r0 + warp + 8 * i];
-                        const float4* __restrict__ src = tbl + ((ea & 0xffff) * T + s_env[ea >> 16].row0) + lane;
-                        if (w0 && !(p.debug_skip & 2)) tr.fv[i][0] = ld_keep4(src, pol_keep);
-                        if (w1 && !(p.debug_skip & 2)) tr.fv[i][1] = ld_keep4(src + 32, pol_keep);
-                    }
-                }
-                if (!PARTIAL || lane < nr) {
-                    const int ea = s_ea[r0 + lane];
-                    const int el = ea >> 16;
-                    const GroupEnv ge = s_env[el];
-                    const float* __restrict__ base = hist_g + (el * WA + (ea & 0xffff));
-                    const float fresh = s_wnew[r0 + lane];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int slot = warp + 8 * j - ge.shift;
-                        float v = 0.0f;
-                        if (j < nj && slot >= 0 && !(p.debug_skip & 1)) v = (slot == ge.fresh_slot) ? fresh : ld_once(base + slot * A, pol_once);
-                        tr.wv[j] = v;
-                    }
-                }
-            };
-            auto spill_tile = [&](const TileRegs& tr, float* __restrict__ tile, int r0, auto partial) {
-                constexpr bool PARTIAL = decltype(partial)::value;
-                const int nr = PARTIAL ? min(32, R - r0) : 32;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (!PARTIAL || warp + 8 * i < nr) {
-                        float* d = tile + fbase + i * fstep;
-                        if (w0) { const float4 v = tr.fv[i][0]; d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
-                        if (w1) { const float4 v = tr.fv[i][1]; d[160] = v.x; d[161] = v.y; d[162] = v.z; d[163] = v.w; }
-                    }
-                }
-                if (!PARTIAL || lane < nr) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j < nj) tile[wbase + 40 * j] = tr.wv[j];
-                }
-            };
-            const int nfull = R >> 5;                      // tiles with all 32 asset-rows
-            auto prefetch = [&](TileRegs& tr, int tj) {   // issue the loads of tile tj (if any) into tr
-                if (tj < ntiles) {
-                    if (tj < nfull) load_tile(tr, tj * 32, std::false_type{}); else load_tile(tr, tj * 32, std::true_type{});
-                }
-            };
-            auto emit = [&](TileRegs& tr, int ti) {       // registers → shared tile → TMA store; refill tr DEPTH tiles ahead
-                float* const tile = buf ? tile1 : tile0;
-                if (tid == 0) bulk_wait_read<1>();        // the store that last used this buffer has drained
-                __syncthreads();
-                const int r0 = ti * 32;
-                if (ti < nfull) spill_tile(tr, tile, r0, std::false_type{}); else spill_tile(tr, tile, r0, std::true_type{});
-                prefetch(tr, ti + DEPTH);                 // these loads fly during the barrier, the store and DEPTH-1 tiles
-                fence_proxy_async_smem();
-                __syncthreads();
-                const int nr = min(32, R - r0);
-                float* const gdst = obs_grp + (size_t)r0 * row_floats;
-                const int n = nr * W * 5;
-                if (p.debug_skip & 4) {
-                } else if (((((uintptr_t)gdst) | ((size_t)n * 4)) & 15) == 0) {
-                    if (tid == 0) { bulk_store_s2g(gdst, tile, (uint32_t)n * 4u, pol_once); bulk_commit(); }
-                } else {
-                    for (int q = tid; q < n; q += kFusedThreads) gdst[q] = tile[q];
-                }
-                buf ^= 1;
-            };
-            TileRegs trA, trB;
-            prefetch(trA, 0);
-            if (DEPTH == 2) prefetch(trB, 1);
-            for (int ti = 0; ti < ntiles; ti += DEPTH) {
-                emit(trA, ti);
-                if (DEPTH == 2 && ti + 1 < ntiles) emit(trB, ti + 1);
-            }
-        } else {
         for (int ti = 0; ti < ntiles; ++ti) {
             float* const tile = buf ? tile1 : tile0;
             if (tid == 0) bulk_wait_read<1>();            // the store that last used this buffer has drained
@@ -328,7 +223,6 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const Step
                 for (int q = tid; q < n; q += kFusedThreads) gdst[q] = tile[q];
             }
             buf ^= 1;
-        }
         }
     }
     if (tid == 0) bulk_wait_read<0>();
@@ -445,7 +339,7 @@ static int launch_step_npl(const StepParams& p, int npl, cudaStream_t s) {
 }
 
 // Fused Mode-O launch: tile rows, group size and grid from the shape (tunable through pmrl_set_tuning).
-static int g_tune_rows = 0, g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1, g_tune_fast = 1, g_tune_depth = 1, g_tune_skip = 0, g_tune_tma = 0, g_tune_stages = 0;
+static int g_tune_rows = 0, g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1, g_tune_fast = 1, g_tune_tma = 0, g_tune_stages = 0;
 
 extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
     switch (key) {
@@ -454,74 +348,64 @@ extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
         case PMRL_TUNE_CTAS_PER_SM: g_tune_ctas_per_sm = value; return 0;
         case PMRL_TUNE_FUSED: g_tune_fused = value; return 0;
         case PMRL_TUNE_FAST_FILL: g_tune_fast = value; return 0;
-        case PMRL_TUNE_PREFETCH_DEPTH: g_tune_depth = value; return 0;
-        case PMRL_TUNE_DEBUG_SKIP: g_tune_skip = value; return 0;
         case PMRL_TUNE_TMA_PIPELINE: g_tune_tma = value; return 0;
         case PMRL_TUNE_TMA_STAGES: g_tune_stages = value; return 0;
         default: return pmrl_fail(PMRL_E_ARG, "unknown tuning key");
     }
 }
 
-template <int NPL, bool HASC, int MINB, bool FAST, int DEPTH>
+template <int NPL, bool HASC, int MINB>
 static int launch_fused_t(StepParams& p, size_t smem, int grid, cudaStream_t s) {
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs<NPL, HASC, MINB, FAST, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs<NPL, HASC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return pmrl_fail((int)e, "cudaFuncSetAttribute(k_env_step_obs) failed");
         attr_done[dev] = true;
     }
-    k_env_step_obs<NPL, HASC, MINB, FAST, DEPTH><<<grid, kFusedThreads, smem, s>>>(p);
+    k_env_step_obs<NPL, HASC, MINB><<<grid, kFusedThreads, smem, s>>>(p);
     return pmrl_check_launch("k_env_step_obs");
 }
 
-template <bool HASC, bool FAST>
+template <bool HASC>
 static int launch_fused_npl(StepParams& p, size_t smem, int grid, int npl, cudaStream_t s) {
-    if (FAST && g_tune_depth == 2) {                 // two tiles of loads in flight per thread (128 registers, 2 CTAs/SM)
-        switch (npl) {
-            case 1: return launch_fused_t<1, HASC, 2, FAST, 2>(p, smem, grid, s);
-            case 2: return launch_fused_t<2, HASC, 2, FAST, 2>(p, smem, grid, s);
-            case 4: return launch_fused_t<4, HASC, 2, FAST, 2>(p, smem, grid, s);
-            default: break;
-        }
-    }
     switch (npl) {
-        case 1: return launch_fused_t<1, HASC, 3, FAST, 1>(p, smem, grid, s);
-        case 2: return launch_fused_t<2, HASC, 3, FAST, 1>(p, smem, grid, s);
-        case 4: return launch_fused_t<4, HASC, 3, FAST, 1>(p, smem, grid, s);
-        case 8: return launch_fused_t<8, HASC, 2, FAST, 1>(p, smem, grid, s);
-        case 16: return launch_fused_t<16, HASC, 1, FAST, 1>(p, smem, grid, s);
-        default: return launch_fused_t<32, HASC, 1, FAST, 1>(p, smem, grid, s);
+        case 1: return launch_fused_t<1, HASC, 3>(p, smem, grid, s);
+        case 2: return launch_fused_t<2, HASC, 3>(p, smem, grid, s);
+        case 4: return launch_fused_t<4, HASC, 3>(p, smem, grid, s);
+        case 8: return launch_fused_t<8, HASC, 2>(p, smem, grid, s);
+        case 16: return launch_fused_t<16, HASC, 1>(p, smem, grid, s);
+        default: return launch_fused_t<32, HASC, 1>(p, smem, grid, s);
     }
 }
 
 static int launch_fused(StepParams& p, float* obs, int npl, cudaStream_t s) {
     p.obs = obs; p.obs_mode = PMRL_OBS_FULL;
-    p.debug_skip = g_tune_skip;
-    if (g_tune_tma && g_tune_fast) {                  // warp-specialised TMA pipeline (env_step_tma.cu)
+    if (g_tune_fast && g_tune_tma) {                  // warp-specialised TMA pipeline (env_step_tma.cu)
         const int rc = pmrl_launch_step_obs_tma(p, npl, g_tune_stages, g_tune_group, s);
         if (rc != -100) return rc;                    // -100: shape not covered by that variant → fall through
     }
+    if (g_tune_fast && (g_tune_rows <= 0 || g_tune_rows == 32)) {   // register-staged fill (env_step_fast.cu): F == 5, W <= 64, A <= 128
+        const int rc = pmrl_launch_step_obs_fast(p, npl, g_tune_group, g_tune_ctas_per_sm, s);
+        if (rc != -100) return rc;
+    }
+    // generic shapes
     const size_t row_bytes = (size_t)p.W * p.F * 4;
     int rows = g_tune_rows > 0 ? g_tune_rows : 32;
     while (rows > 1 && rows * row_bytes > 36 * 1024) rows >>= 1;
     p.tile_assets = rows;
-    // register-staged, software-pipelined fill for the reference obs shape family
-    const bool fast = (p.F == 5) && (p.W <= 64) && (rows == 32) && g_tune_fast && ((size_t)p.A * p.T < (1u << 31)) && p.A < 65536;
-    int ctas_per_sm = g_tune_ctas_per_sm > 0 ? g_tune_ctas_per_sm : (npl <= 4 ? (fast && g_tune_depth == 2 ? 2 : 3) : (npl <= 8 ? 2 : 1));
+    int ctas_per_sm = g_tune_ctas_per_sm > 0 ? g_tune_ctas_per_sm : (npl <= 4 ? 3 : (npl <= 8 ? 2 : 1));
     const int slots = pmrl_sm_count() * ctas_per_sm;
     int G = g_tune_group > 0 ? g_tune_group : kMaxGroup;
     if (G > kMaxGroup) G = kMaxGroup;
     while (G > 1 && (p.E + G - 1) / G < 2 * slots) G >>= 1;     // small batches: more, smaller groups
     p.group_envs = G;
-    const size_t smem = 2 * rows * row_bytes + (size_t)G * p.A * 8;
+    const size_t smem = 2 * rows * row_bytes + (size_t)G * p.A * 4;
     if (smem > 200 * 1024) return pmrl_fail(PMRL_E_SHAPE, "fused step: shared-memory budget exceeded");
     const int n_groups = (p.E + G - 1) / G;
     const int grid = n_groups < slots ? n_groups : slots;
-    const bool hasc = p.commission > 0.0f;
-    if (fast) return hasc ? launch_fused_npl<true, true>(p, smem, grid, npl, s) : launch_fused_npl<false, true>(p, smem, grid, npl, s);
-    return hasc ? launch_fused_npl<true, false>(p, smem, grid, npl, s) : launch_fused_npl<false, false>(p, smem, grid, npl, s);
+    return p.commission > 0.0f ? launch_fused_npl<true>(p, smem, grid, npl, s) : launch_fused_npl<false>(p, smem, grid, npl, s);
 }
 
 extern "C" int pmrl_env_reset(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,

@@ -6,3 +6,6 @@
 // Warp-specialised TMA pipeline variant of the fused step+obs kernel (env_step_tma.cu).
 // Returns -100 if the shape is not supported by this variant (caller falls back).
 int pmrl_launch_step_obs_tma(pmrl::StepParams& p, int npl, int stages, int group, cudaStream_t s);
+
+// Register-staged fused step+obs kernel (env_step_fast.cu).  Returns -100 if the shape is not covered.
+int pmrl_launch_step_obs_fast(pmrl::StepParams& p, int npl, int group, int ctas_per_sm, cudaStream_t s);

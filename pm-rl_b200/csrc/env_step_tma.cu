@@ -166,19 +166,17 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_env_step_obs_tma(const StepP
             cw.init(lane, A);
             float wv[8], fresh = 0.0f;
             int wf = -1;                                                // window column that shows the fresh ring row
-            auto load_ring = [&](int r0) {                              // ring rows of tile r0 → registers (branch-free)
-                if (r0 + lane < R) {
-                    const GroupEnvT ge = env_b[cw.el];
+            int shift_r = 0;                                            // ring shift of the env whose rows sit in wv[]
+            auto load_ring = [&](int r0) {                              // ring rows of tile r0 → registers; nothing here
+                if (r0 + lane < R) {                                    // consumes the loaded values (they are used one
+                    const GroupEnvT ge = env_b[cw.el];                  // tile later), so the DRAM latency stays hidden
                     const float* __restrict__ base = hist_g + (cw.el * WA + cw.a);
                     fresh = wnew_b[r0 + lane];
                     wf = ge.fresh_slot + ge.shift;
+                    shift_r = ge.shift;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int slot = warp + 8 * j - ge.shift;
-                        float v = 0.0f;
-                        if (j < nj) v = ld_once_c(base + max(slot, 0) * A);
-                        wv[j] = slot >= 0 ? v : 0.0f;                   // zero front padding while the ring is not full
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        if (j < nj) wv[j] = ld_once_c(base + max(warp + 8 * j - ge.shift, 0) * A);
                 }
                 cw.advance(32, A);
             };
@@ -192,8 +190,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_env_step_obs_tma(const StepP
                 // weight channel from the prefetched registers; the row written by this step from shared memory
                 if (lane < nr) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j < nj) tile[wbase + 40 * j] = wv[j];
+                    for (int j = 0; j < 8; ++j)                         // zero front padding while the ring is not full
+                        if (j < nj) tile[wbase + 40 * j] = (warp + 8 * j >= shift_r) ? wv[j] : 0.0f;
                     if ((wf & 7) == warp) tile[(lane * W + wf) * 5 + 4] = fresh;
                 }
                 if (ti + 1 < ntiles) load_ring(r0 + 32);                // flies during the feature copy, the barrier and the store

@@ -98,13 +98,13 @@ def tuning():
         _lib.set_tuning(k, 0)
     _lib.set_tuning(_lib.TUNE_FUSED, 1)
     _lib.set_tuning(_lib.TUNE_TMA_PIPELINE, DEFAULT_TMA)
-    _lib.set_tuning(_lib.TUNE_PREFETCH_DEPTH, 1)
+    _lib.set_tuning(_lib.TUNE_FAST_FILL, 1)
 
 
 DEFAULT_TMA = 0
-# (fused, tile_rows, group_envs, tma, stages/depth): the fused step+obs kernel in several launch shapes (register-staged
-# fill, two-tile prefetch, warp-specialised TMA pipeline with 2..6 stages) and the two-kernel path
-VARIANTS = [(1, 0, 0, 0, 1), (1, 8, 3, 0, 1), (1, 32, 1, 0, 1), (1, 0, 0, 0, 2), (0, 0, 0, 0, 1),
+# (fused, tile_rows, group_envs, tma, stages | fast): the fused step+obs kernel in several launch shapes (register-staged
+# fast fill, generic fill, warp-specialised TMA pipeline with 2..6 stages) and the two-kernel path
+VARIANTS = [(1, 0, 0, 0, 1), (1, 0, 3, 0, 1), (1, 8, 3, 0, 0), (1, 32, 1, 0, 0), (0, 0, 0, 0, 1),
             (1, 0, 0, 1, 4), (1, 0, 2, 1, 2), (1, 0, 8, 1, 6)]
 
 
@@ -121,7 +121,7 @@ def test_table_driven_step_and_obs_vs_oracle(A, W, F, E, variant, tuning):
     if tma:
         tuning.set_tuning(tuning.TUNE_TMA_STAGES, depth)
     else:
-        tuning.set_tuning(tuning.TUNE_PREFETCH_DEPTH, depth)
+        tuning.set_tuning(tuning.TUNE_FAST_FILL, depth)
     L = W + 7
     gpu, ora = make_pair(E, A, W, F, episode_len=L)
     g = torch.Generator().manual_seed(99)

@@ -230,3 +230,40 @@ def test_eval_metrics_vs_numpy():
     to = np.abs(np.diff(w.astype(np.float64), axis=1)).sum(-1).mean(1)        # util/eval.py:32-37
     np.testing.assert_allclose(got[:, 0], sharpe, rtol=1e-4); np.testing.assert_allclose(got[:, 1], sortino, rtol=1e-4)
     np.testing.assert_allclose(got[:, 2], mdd, rtol=1e-5, atol=1e-6); np.testing.assert_allclose(got[:, 3], to, rtol=1e-5)
+
+
+# ---------------------------------------------------------------- collect loops (N1)
+def test_collect_loops_drive_env_and_buffers():
+    import pmrl_b200
+    from pmrl_b200 import loops, synth
+    from pmrl_b200.buffers import DeviceReplayBuffer, DeviceRolloutBuffer
+    from pmrl_b200.env import BatchedTradingEnv
+    from oracle.env_oracle import OracleEnv
+    E, A, W, F, items = 6, 9, 5, 5, 30
+    tbl = synth.gbm_ohlc(128, A)
+    cfg = pmrl_b200.EnvConfig(num_envs=E, num_assets=A, window_size=W, episode_len=items)
+    env = BatchedTradingEnv(cfg, prices=tbl)
+    torch.manual_seed(0)
+    proj = torch.randn(W * F, device="cuda") * 0.1
+    act_fn = lambda s: (s.reshape(E, A, W * F) @ proj)                       # a deterministic "policy": [E, A] raw scores
+    buf = DeviceRolloutBuffer(F, items, E, A, W, batch_size=4)
+    loops.collect_on_policy(env, act_fn, buf, items)
+    # replay the same loop against the oracle with the actions the policy produced from the oracle's own obs
+    ora = OracleEnv(E, A, W, F, close=tbl[:, :, 3].numpy(), feat=tbl.numpy(), episode_len=items)
+    s = ora.obs()
+    for step in range(1, items):
+        a = act_fn(torch.from_numpy(s).cuda()).cpu().numpy()
+        slot = step - (W - 1)
+        if slot > 0:
+            np.testing.assert_allclose(buf.s[slot].cpu().numpy(), s, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(buf.a[slot].cpu().numpy(), a, rtol=1e-4, atol=1e-6)
+        r, _ = ora.step(a)
+        if slot > 0:
+            np.testing.assert_allclose(buf.r[slot].cpu().numpy(), r, rtol=1e-4, atol=1e-6)
+            np.testing.assert_allclose(buf.v[slot].cpu().numpy(), ora.value, rtol=1e-5)
+        s = ora.obs()
+    rb = DeviceReplayBuffer(env.feat_am, F, items, E, A, W, buffer_size=3 * items, batch_size=4)
+    loops.collect_off_policy(env, act_fn, rb, 0, items)
+    assert int(rb.bi[0, 0, 0]) == 2 * (W - 1) and int(rb.bi[0, -1, 0]) == items - 1
+    total, met = loops.evaluate(env, act_fn, items)
+    assert total.shape == (E,) and met.shape == (E, 4) and torch.isfinite(met).all()
