@@ -350,6 +350,7 @@ extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
         case PMRL_TUNE_FAST_FILL: g_tune_fast = value; return 0;
         case PMRL_TUNE_TMA_PIPELINE: g_tune_tma = value; return 0;
         case PMRL_TUNE_TMA_STAGES: g_tune_stages = value; return 0;
+        case PMRL_TUNE_FAST_VARIANT: pmrl_set_fast_variant(value); return 0;
         default: return pmrl_fail(PMRL_E_ARG, "unknown tuning key");
     }
 }

@@ -1,18 +1,25 @@
 // env_step_fast.cu — fused step + observation kernel, register-staged fill (the default Mode-O path for F == 5, W <= 64).
 //
 // A persistent CTA (3 per SM) owns a group of G <= 8 consecutive envs at a time:
-//   phase 1  warp w advances env e0+w in registers (env_step_warp: trading_env.py:54-100) and leaves, per asset-row
-//            of the group, w' and the table offset of its feature window in shared memory;
+//   phase 1  warp w advances env e0+w in registers (env_step_warp: trading_env.py:54-100) and leaves w', the ring
+//            pointer and the window row of the env in shared memory;
 //   phase 2  the group's obs is one contiguous [G*A, W, 5] slab; it is streamed as 32-asset-row tiles (cut across
 //            env boundaries).  A thread owns a fixed set of 8 float4 table loads + 8 ring loads per tile; all 16
 //            are issued back to back, and the loads of tile i+1 are issued before tile i is handed to the TMA
-//            store engine, so L2/DRAM latency overlaps the shared-memory interleave, the barriers and the store.
-//            The tile in shared memory is the exact byte image of obs[e, a0:a0+32, :, :] and leaves as ONE
-//            cp.async.bulk (UBLKCP) store with an L2 evict_first hint.
-// The window size is a template parameter for the common W (50, 32) so that every shared-memory offset and
-// loop bound of the hot loop is an immediate; WT == 0 is the runtime-W instance.
+//            store engine.  The tile in shared memory is the exact byte image of obs[e, a0:a0+32, :, :] and leaves
+//            as ONE cp.async.bulk (UBLKCP) store with an L2 evict_first hint while the next tile is being filled.
 // Weight channel semantics: ActionBuffer.get_all (weight_buffer.py:32-44) — zero front padding while the ring is not
 // full, raw ring order once it is; the row written by this very step comes from shared memory, never from global.
+//
+// Template knobs (PMRL_TUNE_FAST_VARIANT selects them for A/B measurement; the defaults are the measured best):
+//   WT     window size as a compile-time constant (50, 32) so every shared-memory offset of the hot loop is an
+//          immediate; 0 = runtime W
+//   RING2  the ring rows are prefetched TWO tiles ahead (8 registers per tile) and always issued after the table
+//          loads of the next tile: the L1 returns loads in issue order, so DRAM-latency ring loads queued in front
+//          of L2-hit table loads would make every load of the tile wait for DRAM
+// Measured dead ends (see profiles/): resolving the zero padding / fresh row when the tile is written instead of
+// when it is loaded (predicated, branch-free loads) lets ptxas hoist the ring loads in front of the table loads
+// (3.2 → 4.4 ms); writing the tile out with plain 16-byte stores instead of the TMA bulk store (5.0 ms).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <type_traits>
@@ -24,51 +31,32 @@
 
 namespace pmrl {
 
-constexpr int kFastThreads = 256;
-constexpr int kFastWarps = kFastThreads / 32;
-constexpr int kFastGroup = kFastWarps;
+constexpr int kFusedThreads = 256;
+constexpr int kFusedWarps = kFusedThreads / 32;
+constexpr int kMaxGroup = kFusedWarps;
 
-struct FastEnv { int shift, wf; };        // per env of the group: ring shift and the window column of the fresh row
+struct GroupEnv { int row0, shift, fresh_slot, pad; };   // per env of the group (phase 1 → phase 2)
 
-struct FastRegs {                         // one tile's worth of in-flight loads of a thread
-    float4 fv[4][2];
-    float wv[8];
-    float fresh;
-    int shift, wf;
-};
+struct FeatRegs { float4 fv[4][2]; };     // one tile of in-flight table loads of a thread
+struct RingRegs { float wv[8]; };         // one tile of in-flight ring loads of a thread
 
-__device__ __forceinline__ float4 ld_table4(const float4* p) {      // table rows: keep in L2 (constant evict_last policy)
-    float4 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(kPolicyEvictLast));
-    return v;
-}
-
-template <int NPL, bool HASC, int WT>
-__global__ void __launch_bounds__(kFastThreads, 3) k_env_step_obs_fast(const StepParams p) {
+template <int NPL, bool HASC, int WT, bool RING2, int MINB>
+__global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs_fast(const StepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ double s_stats[kFastWarps * PMRL_STATS_LEN];
-    __shared__ FastEnv s_env[kFastGroup];
+    __shared__ double s_stats[kFusedWarps * PMRL_STATS_LEN];
+    __shared__ GroupEnv s_env[kMaxGroup];
     const int W = WT ? WT : p.W;
     const int A = p.A, T = p.T, G = p.group_envs;
     const int tile_floats = 32 * W * 5;
     float* const tile0 = reinterpret_cast<float*>(smem_raw);
     float* const tile1 = tile0 + tile_floats;
-    float* const s_wnew = tile1 + tile_floats;                    // [G*A]  w' per asset-row of the group
-    int* const s_roff = reinterpret_cast<int*>(s_wnew + G * A);   // [G*A]  float4 offset of the asset-row's window in feat_am
+    float* const s_wnew = tile1 + tile_floats;           // [G, A]   w' of the group's envs, indexed by asset-row
+    int* const s_ea = reinterpret_cast<int*>(s_wnew + G * A);   // [G, A]   (env-in-group << 16) | asset per asset-row
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_groups = (p.E + G - 1) / G;
-    const int WA = W * A;
-    if (p.stats) stats_init_block(s_stats, kFastWarps);
-
-    // thread-invariant shared-memory offsets: features rows warp+8i (i<4) × window rows lane, lane+32;
-    // weights: asset-row = lane, window columns warp+8j (j<8)
-    const int fbase = (warp * W + lane) * 5;
-    const int wbase = (lane * W + warp) * 5 + 4;
-    const bool w0 = lane < W, w1 = lane + 32 < W;
-    const int nj = min(8, max(0, (W - warp + 7) >> 3));
-    const float4* __restrict__ tbl = reinterpret_cast<const float4*>(p.feat_am) + lane;
-
+    const size_t row_floats = (size_t)W * 5;
+    if (p.stats) stats_init_block(s_stats, kFusedWarps);
+    const uint64_t pol_keep = kPolicyEvictLast, pol_once = kPolicyEvictFirst;   // immediates: no per-load register moves
     int buf = 0;
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int e0 = grp * G;
@@ -79,128 +67,156 @@ __global__ void __launch_bounds__(kFastThreads, 3) k_env_step_obs_fast(const Ste
             EnvVectors<NPL, HASC> ev;
             StepOut so;
             env_step_warp<NPL, HASC>(p, e, lane, ev, so, s_stats + warp * PMRL_STATS_LEN);
-            const int row0 = p.t0[e] + so.k;
 #pragma unroll
             for (int j = 0; j < NPL; ++j) {
                 const int a = lane + 32 * j;
-                if (a < A) { s_wnew[warp * A + a] = ev.a[j]; s_roff[warp * A + a] = a * T + row0; }
+                if (a < A) { s_wnew[warp * A + a] = ev.a[j]; s_ea[warp * A + a] = (warp << 16) | a; }
             }
             if (lane == 0) {
-                FastEnv fe;
-                fe.shift = so.is_full ? 0 : (W - so.idx_new);                          // weight_buffer.py:38-42
-                fe.wf = (so.did_reset ? 0 : so.slot_written) + fe.shift;               // column showing the row of this step
-                s_env[warp] = fe;
+                GroupEnv ge;
+                ge.row0 = p.t0[e] + so.k;
+                ge.shift = so.is_full ? 0 : (W - so.idx_new);            // weight_buffer.py:38-42
+                ge.fresh_slot = so.did_reset ? 0 : so.slot_written;       // rows written by this launch come from smem
+                ge.pad = 0;
+                s_env[warp] = ge;
             }
         }
         __syncthreads();
-        // ---------------- phase 2: 32-asset-row tiles over the group's [ne*A] rows ----------------
+        // ---------------- phase 2: tiles over the group's [ne*A] asset-rows ----------------
         const int R = ne * A;
-        const int ntiles = (R + 31) >> 5, nfull = R >> 5;
-        const float* __restrict__ hist_g = p.hist + (size_t)e0 * WA;
-        float* gdst = p.obs + (size_t)e0 * A * (W * 5);
-        int wel = lane / A, wa = lane - wel * A;                   // (env-in-group, asset) of this lane's weight row
-
-        auto load_tile = [&](FastRegs& tr, int r0, auto partial) {
-            constexpr bool PARTIAL = decltype(partial)::value;
-            const int nr = PARTIAL ? R - r0 : 32;
+        const int ntiles = (R + 31) >> 5;
+        float* const obs_grp = p.obs + (size_t)e0 * A * row_floats;
+        {
+            const float4* __restrict__ tbl = reinterpret_cast<const float4*>(p.feat_am);
+            const float* __restrict__ hist_g = p.hist + (size_t)e0 * W * A;
+            // thread-invariant shared-memory offsets of this thread's 8 feature rows / 8 weight columns
+            const int fbase = (warp * W + lane) * 5, fstep = 8 * W * 5;
+            const bool w0 = lane < W, w1 = lane + 32 < W;
+            const int wbase = (lane * W + warp) * 5 + 4;
+            const int nj = min(8, max(0, (W - warp + 7) >> 3));
+            const int WA = W * A;
+            auto load_feat = [&](FeatRegs& fr, int r0, auto partial) {
+                constexpr bool PARTIAL = decltype(partial)::value;
+                const int nr = PARTIAL ? R - r0 : 32;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (!PARTIAL || warp + 8 * i < nr) {
-                    const float4* __restrict__ src = tbl + s_roff[r0 + warp + 8 * i];
-                    if (w0) tr.fv[i][0] = ld_table4(src);
-                    if (w1) tr.fv[i][1] = ld_table4(src + 32);
+                for (int i = 0; i < 4; ++i) {
+                    if (!PARTIAL || warp + 8 * i < nr) {
+                        const int ea = s_ea[r0 + warp + 8 * i];
+                        const float4* __restrict__ src = tbl + ((ea & 0xffff) * T + s_env[ea >> 16].row0) + lane;
+                        if (w0) fr.fv[i][0] = ld_keep4(src, pol_keep);
+                        if (w1) fr.fv[i][1] = ld_keep4(src + 32, pol_keep);
+                    }
                 }
-            }
-            if (!PARTIAL || lane < nr) {
-                const FastEnv fe = s_env[wel];
-                const float* __restrict__ base = hist_g + (wel * WA + wa);
-                tr.fresh = s_wnew[r0 + lane];
-                tr.shift = fe.shift;
-                tr.wf = fe.wf;
+            };
+            auto load_ring = [&](RingRegs& rr, int r0) {       // zero padding / fresh row resolved here, at load time
+                if (r0 + lane < R) {
+                    const int ea = s_ea[r0 + lane];
+                    const int el = ea >> 16;
+                    const GroupEnv ge = s_env[el];
+                    const float* __restrict__ base = hist_g + (el * WA + (ea & 0xffff));
+                    const float fresh = s_wnew[r0 + lane];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)                        // raw ring values; padding / fresh row are resolved at spill time
-                    if (j < nj) tr.wv[j] = ld_once_c(base + max(warp + 8 * j - fe.shift, 0) * A);
-            }
-            wa += 32;
-            while (wa >= A) { wa -= A; ++wel; }
-        };
-        auto spill_tile = [&](const FastRegs& tr, float* __restrict__ tile, int r0, auto partial) {
-            constexpr bool PARTIAL = decltype(partial)::value;
-            const int nr = PARTIAL ? R - r0 : 32;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (!PARTIAL || warp + 8 * i < nr) {
-                    float* d = tile + fbase + i * (8 * W * 5);
-                    if (w0) { const float4 v = tr.fv[i][0]; d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
-                    if (w1) { const float4 v = tr.fv[i][1]; d[160] = v.x; d[161] = v.y; d[162] = v.z; d[163] = v.w; }
+                    for (int j = 0; j < 8; ++j) {
+                        const int slot = warp + 8 * j - ge.shift;
+                        float v = 0.0f;
+                        if (j < nj && slot >= 0) v = (slot == ge.fresh_slot) ? fresh : ld_once(base + slot * A, pol_once);
+                        rr.wv[j] = v;
+                    }
                 }
-            }
-            if (!PARTIAL || lane < nr) {
+            };
+            auto spill_tile = [&](const FeatRegs& fr, const RingRegs& rr, float* __restrict__ tile, int r0, auto partial) {
+                constexpr bool PARTIAL = decltype(partial)::value;
+                const int nr = PARTIAL ? R - r0 : 32;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (j < nj) tile[wbase + 40 * j] = (warp + 8 * j >= tr.shift) ? tr.wv[j] : 0.0f;
-                if ((tr.wf & 7) == warp) tile[(lane * W + tr.wf) * 5 + 4] = tr.fresh;
+                for (int i = 0; i < 4; ++i) {
+                    if (!PARTIAL || warp + 8 * i < nr) {
+                        float* d = tile + fbase + i * fstep;
+                        if (w0) { const float4 v = fr.fv[i][0]; d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+                        if (w1) { const float4 v = fr.fv[i][1]; d[160] = v.x; d[161] = v.y; d[162] = v.z; d[163] = v.w; }
+                    }
+                }
+                if (!PARTIAL || lane < nr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < nj) tile[wbase + 40 * j] = rr.wv[j];
+                }
+            };
+            const int nfull = R >> 5;                      // tiles with all 32 asset-rows
+            constexpr int RA = RING2 ? 2 : 1;              // ring prefetch distance in tiles
+            auto emit = [&](FeatRegs& fr, RingRegs& rr, int ti) {   // registers → shared tile → TMA store; refill the registers
+                float* const tile = buf ? tile1 : tile0;
+                if (tid == 0) bulk_wait_read<1>();        // the store that last used this buffer has drained
+                __syncthreads();
+                const int r0 = ti * 32;
+                if (ti < nfull) spill_tile(fr, rr, tile, r0, std::false_type{}); else spill_tile(fr, rr, tile, r0, std::true_type{});
+                if (ti + 1 < ntiles) {                    // table loads of the next tile first (L2 hits) ...
+                    if (ti + 1 < nfull) load_feat(fr, r0 + 32, std::false_type{}); else load_feat(fr, r0 + 32, std::true_type{});
+                }
+                if (ti + RA < ntiles) load_ring(rr, r0 + 32 * RA);   // ... then the DRAM-latency ring loads, RA tiles ahead
+                fence_proxy_async_smem();
+                __syncthreads();
+                const int nr = min(32, R - r0);
+                float* const gdst = obs_grp + (size_t)r0 * row_floats;
+                const int n = nr * W * 5;
+                if (((((uintptr_t)gdst) | ((size_t)n * 4)) & 15) == 0) {
+                    if (tid == 0) { bulk_store_s2g(gdst, tile, (uint32_t)n * 4u, pol_once); bulk_commit(); }
+                } else {
+                    for (int q = tid; q < n; q += kFusedThreads) gdst[q] = tile[q];
+                }
+                buf ^= 1;
+            };
+            FeatRegs fr;
+            RingRegs rrA, rrB;
+            if (nfull > 0) load_feat(fr, 0, std::false_type{}); else load_feat(fr, 0, std::true_type{});
+            load_ring(rrA, 0);
+            if (RING2 && ntiles > 1) load_ring(rrB, 32);
+            for (int ti = 0; ti < ntiles; ti += RA) {
+                emit(fr, rrA, ti);
+                if (RING2 && ti + 1 < ntiles) emit(fr, rrB, ti + 1);
             }
-        };
-
-        FastRegs tr;
-        if (nfull > 0) load_tile(tr, 0, std::false_type{}); else load_tile(tr, 0, std::true_type{});
-        for (int ti = 0; ti < ntiles; ++ti) {
-            float* const tile = buf ? tile1 : tile0;
-            if (tid == 0) bulk_wait_read<1>();                     // the store that last used this buffer has drained
-            __syncthreads();
-            const int r0 = ti * 32;
-            if (ti < nfull) spill_tile(tr, tile, r0, std::false_type{}); else spill_tile(tr, tile, r0, std::true_type{});
-            if (ti + 1 < ntiles) {                                 // next tile's loads fly during the barrier and the store
-                if (ti + 1 < nfull) load_tile(tr, r0 + 32, std::false_type{}); else load_tile(tr, r0 + 32, std::true_type{});
-            }
-            fence_proxy_async_smem();
-            __syncthreads();
-            const int n = min(32, R - r0) * W * 5;
-            if (((((uintptr_t)gdst) | ((size_t)n * 4)) & 15) == 0) {
-                if (tid == 0) { bulk_store_s2g(gdst, tile, (uint32_t)n * 4u, kPolicyEvictFirst); bulk_commit(); }
-            } else {
-                for (int q = tid; q < n; q += kFastThreads) gdst[q] = tile[q];
-            }
-            gdst += 32 * W * 5;
-            buf ^= 1;
         }
     }
     if (tid == 0) bulk_wait_read<0>();
-    if (p.stats) stats_flush_block(p.stats, s_stats, kFastWarps);
+    if (p.stats) stats_flush_block(p.stats, s_stats, kFusedWarps);
 }
 
 }  // namespace pmrl
 
 using namespace pmrl;
 
-template <int NPL, bool HASC, int WT>
+static int g_fast_variant = -1;                      // -1 = default (WT from W, RING2 off, 3 CTAs/SM)
+void pmrl_set_fast_variant(int v) { g_fast_variant = v; }
+
+template <int NPL, bool HASC, int WT, bool RING2, int MINB>
 static int launch_fast_t(StepParams& p, size_t smem, int grid, cudaStream_t s) {
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs_fast<NPL, HASC, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs_fast<NPL, HASC, WT, RING2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return pmrl_fail((int)e, "cudaFuncSetAttribute(k_env_step_obs_fast) failed");
         attr_done[dev] = true;
     }
-    k_env_step_obs_fast<NPL, HASC, WT><<<grid, kFastThreads, smem, s>>>(p);
+    k_env_step_obs_fast<NPL, HASC, WT, RING2, MINB><<<grid, kFusedThreads, smem, s>>>(p);
     return pmrl_check_launch("k_env_step_obs_fast");
 }
 
 template <int NPL, bool HASC>
 static int launch_fast_w(StepParams& p, size_t smem, int grid, cudaStream_t s) {
-    if (p.W == 50) return launch_fast_t<NPL, HASC, 50>(p, smem, grid, s);
-    if (p.W == 32) return launch_fast_t<NPL, HASC, 32>(p, smem, grid, s);
-    return launch_fast_t<NPL, HASC, 0>(p, smem, grid, s);
+    if (p.W == 50) return launch_fast_t<NPL, HASC, 50, false, 3>(p, smem, grid, s);
+    if (p.W == 32) return launch_fast_t<NPL, HASC, 32, false, 3>(p, smem, grid, s);
+    return launch_fast_t<NPL, HASC, 0, false, 3>(p, smem, grid, s);
 }
 
 int pmrl_launch_step_obs_fast(StepParams& p, int npl, int group, int ctas_per_sm, cudaStream_t s) {
     if (p.F != 5 || p.W > 64 || npl > 4) return -100;              // larger A: register budget of 3 CTAs/SM does not hold
-    if ((size_t)p.A * p.T >= (1u << 31)) return -100;
-    const int slots = pmrl_sm_count() * (ctas_per_sm > 0 ? ctas_per_sm : 3);
-    int G = group > 0 ? group : kFastGroup;
-    if (G > kFastGroup) G = kFastGroup;
+    if ((size_t)p.A * p.T >= (1u << 31) || p.A >= 65536) return -100;
+    const int var = g_fast_variant;
+    const bool ab = var >= 0 && npl == 4 && p.commission <= 0.0f && p.W == 50;   // A/B variants: benchmark shape only
+    const int minb = (ab && (var & 2)) ? 2 : 3;
+    const int slots = pmrl_sm_count() * (ctas_per_sm > 0 ? ctas_per_sm : minb);
+    int G = group > 0 ? group : kMaxGroup;
+    if (G > kMaxGroup) G = kMaxGroup;
     while (G > 1 && (p.E + G - 1) / G < 2 * slots) G >>= 1;         // small batches: more, smaller groups
     p.group_envs = G;
     p.tile_assets = 32;
@@ -209,6 +225,17 @@ int pmrl_launch_step_obs_fast(StepParams& p, int npl, int group, int ctas_per_sm
     const int n_groups = (p.E + G - 1) / G;
     const int grid = n_groups < slots ? n_groups : slots;
     const bool hasc = p.commission > 0.0f;
+    if (ab) {                                        // bit0: RING2, bit1: 2 CTAs/SM (128 registers), bit2: runtime W
+        switch (var & 7) {
+            case 0: return launch_fast_t<4, false, 50, false, 3>(p, smem, grid, s);
+            case 1: return launch_fast_t<4, false, 50, true, 3>(p, smem, grid, s);
+            case 2: return launch_fast_t<4, false, 50, false, 2>(p, smem, grid, s);
+            case 3: return launch_fast_t<4, false, 50, true, 2>(p, smem, grid, s);
+            case 4: return launch_fast_t<4, false, 0, false, 3>(p, smem, grid, s);
+            case 5: return launch_fast_t<4, false, 0, true, 3>(p, smem, grid, s);
+            default: break;
+        }
+    }
 #define FAST_CASE(N) return hasc ? launch_fast_w<N, true>(p, smem, grid, s) : launch_fast_w<N, false>(p, smem, grid, s)
     switch (npl) {
         case 1: FAST_CASE(1);

@@ -175,8 +175,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_env_step_obs_tma(const StepP
                     wf = ge.fresh_slot + ge.shift;
                     shift_r = ge.shift;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j < nj) wv[j] = ld_once_c(base + max(warp + 8 * j - ge.shift, 0) * A);
+                    for (int j = 0; j < 8; ++j) {                       // never load the row this launch has just written
+                        const int cs = max(warp + 8 * j - ge.shift, 0);   // (patched from smem; a load hitting the in-flight
+                        if (j < nj && cs != ge.fresh_slot) wv[j] = ld_once_c(base + cs * A);   // store stalls the L1 queue)
+                    }
                 }
                 cw.advance(32, A);
             };

@@ -244,7 +244,7 @@ def test_collect_loops_drive_env_and_buffers():
     cfg = pmrl_b200.EnvConfig(num_envs=E, num_assets=A, window_size=W, episode_len=items)
     env = BatchedTradingEnv(cfg, prices=tbl)
     torch.manual_seed(0)
-    proj = torch.randn(W * F, device="cuda") * 0.1
+    proj = torch.randn(W * F, device="cuda") * 2e-3                          # prices ~1e2 → raw scores of order 1
     act_fn = lambda s: (s.reshape(E, A, W * F) @ proj)                       # a deterministic "policy": [E, A] raw scores
     buf = DeviceRolloutBuffer(F, items, E, A, W, batch_size=4)
     loops.collect_on_policy(env, act_fn, buf, items)
@@ -266,4 +266,5 @@ def test_collect_loops_drive_env_and_buffers():
     loops.collect_off_policy(env, act_fn, rb, 0, items)
     assert int(rb.bi[0, 0, 0]) == 2 * (W - 1) and int(rb.bi[0, -1, 0]) == items - 1
     total, met = loops.evaluate(env, act_fn, items)
-    assert total.shape == (E,) and met.shape == (E, 4) and torch.isfinite(met).all()
+    assert total.shape == (E,) and met.shape == (E, 4) and torch.isfinite(met).all() and torch.isfinite(total).all()
+    assert np.isfinite(ora.value).all()
