@@ -48,6 +48,16 @@ def algorithmic_bytes_per_asset_step(A, W, F, commission, obs):
     return b + (4.0 if commission > 0 else 0.0)
 
 
+def ncu_traffic_bytes(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture of this workload (profiles/traffic.json), or None if no capture exists for it."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -274,8 +284,9 @@ def main():
                        "l2_policy": "working set per step (obs write + ring) exceeds L2 (126 MB)" if E * A * W * 4 > 126e6
                                     else "working set smaller than L2: L2-resident by construction"},
             "roofline": {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak,
-                         "traffic": None, "bytes_per_asset_step": bpa, "peak_source": peak_src,
-                         "kernel": "k_env_step_obs" if obs else "k_env_step"},
+                         "traffic": ncu_traffic_bytes(args.workload), "algorithmic_bytes_per_launch": bpa * E * A,
+                         "bytes_per_asset_step": bpa, "peak_source": peak_src,
+                         "kernel": "k_env_step_obs_fast" if obs else "k_env_step"},
             "clocks": clocks,
             "gpu_launches": launches_per_step * args.steps,
             "stats": {k: stats[k] for k in ("n_envs", "mean_reward", "mean_value", "n_done")},
