@@ -14,12 +14,13 @@
 // Template knobs (PMRL_TUNE_FAST_VARIANT selects them for A/B measurement; the defaults are the measured best):
 //   WT     window size as a compile-time constant (50, 32) so every shared-memory offset of the hot loop is an
 //          immediate; 0 = runtime W
-//   RING2  the ring rows are prefetched TWO tiles ahead (8 registers per tile) and always issued after the table
-//          loads of the next tile: the L1 returns loads in issue order, so DRAM-latency ring loads queued in front
-//          of L2-hit table loads would make every load of the tile wait for DRAM
-// Measured dead ends (see profiles/): resolving the zero padding / fresh row when the tile is written instead of
-// when it is loaded (predicated, branch-free loads) lets ptxas hoist the ring loads in front of the table loads
-// (3.2 → 4.4 ms); writing the tile out with plain 16-byte stores instead of the TMA bulk store (5.0 ms).
+//   RING2  (variant) predicated branch-free ring loads kept behind the table loads by a warp barrier: the L1 returns
+//          loads in issue order, so DRAM-latency ring loads queued in front of L2-hit table loads make every load
+//          of the tile wait for DRAM
+// Measured: predicated branch-free ring loads WITHOUT the warp barrier let ptxas hoist them in front of
+// the table loads (3.2 → 4.4 ms); with it they tie with the branchy form (3.27 vs 3.26 ms); 2 CTAs/SM at 123 registers
+// without spills ties with 3 CTAs/SM at 80 (3.29 ms); issuing the proxy fence before the prefetch loads changes nothing;
+// writing the tile out with plain 16-byte stores instead of the TMA bulk store is slower (5.0 ms).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <type_traits>
@@ -38,7 +39,7 @@ constexpr int kMaxGroup = kFusedWarps;
 struct GroupEnv { int row0, shift, fresh_slot, pad; };   // per env of the group (phase 1 → phase 2)
 
 struct FeatRegs { float4 fv[4][2]; };     // one tile of in-flight table loads of a thread
-struct RingRegs { float wv[8]; };         // one tile of in-flight ring loads of a thread
+struct RingRegs { float wv[8]; float fresh; int shift, wf; };   // one tile of in-flight ring loads of a thread
 
 template <int NPL, bool HASC, int WT, bool RING2, int MINB>
 __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs_fast(const StepParams p) {
@@ -108,19 +109,31 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs_fast(const
                     }
                 }
             };
-            auto load_ring = [&](RingRegs& rr, int r0) {       // zero padding / fresh row resolved here, at load time
+            auto load_ring = [&](RingRegs& rr, int r0) {
                 if (r0 + lane < R) {
                     const int ea = s_ea[r0 + lane];
                     const int el = ea >> 16;
                     const GroupEnv ge = s_env[el];
                     const float* __restrict__ base = hist_g + (el * WA + (ea & 0xffff));
                     const float fresh = s_wnew[r0 + lane];
+                    if constexpr (RING2) {
+                        // predicated loads (no branch per row); zero padding and the fresh row are resolved when the tile is
+                        // written.  The caller separates them from the table loads with a warp barrier so that ptxas cannot
+                        // hoist these DRAM-latency loads in front of the L2-hit table loads (the L1 returns in issue order).
+                        rr.fresh = fresh; rr.shift = ge.shift; rr.wf = ge.fresh_slot + ge.shift;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int slot = warp + 8 * j - ge.shift;
-                        float v = 0.0f;
-                        if (j < nj && slot >= 0) v = (slot == ge.fresh_slot) ? fresh : ld_once(base + slot * A, pol_once);
-                        rr.wv[j] = v;
+                        for (int j = 0; j < 8; ++j) {
+                            const int cs = max(warp + 8 * j - ge.shift, 0);
+                            if (j < nj && cs != ge.fresh_slot) rr.wv[j] = ld_once(base + cs * A, pol_once);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {             // zero padding / fresh row resolved here, at load time
+                            const int slot = warp + 8 * j - ge.shift;
+                            float v = 0.0f;
+                            if (j < nj && slot >= 0) v = (slot == ge.fresh_slot) ? fresh : ld_once(base + slot * A, pol_once);
+                            rr.wv[j] = v;
+                        }
                     }
                 }
             };
@@ -138,11 +151,12 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs_fast(const
                 if (!PARTIAL || lane < nr) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        if (j < nj) tile[wbase + 40 * j] = rr.wv[j];
+                        if (j < nj) tile[wbase + 40 * j] = RING2 ? ((warp + 8 * j >= rr.shift) ? rr.wv[j] : 0.0f) : rr.wv[j];
+                    if constexpr (RING2) { if ((rr.wf & 7) == warp) tile[(lane * W + rr.wf) * 5 + 4] = rr.fresh; }
                 }
             };
             const int nfull = R >> 5;                      // tiles with all 32 asset-rows
-            constexpr int RA = RING2 ? 2 : 1;              // ring prefetch distance in tiles
+            constexpr int RA = 1;
             auto emit = [&](FeatRegs& fr, RingRegs& rr, int ti) {   // registers → shared tile → TMA store; refill the registers
                 float* const tile = buf ? tile1 : tile0;
                 if (tid == 0) bulk_wait_read<1>();        // the store that last used this buffer has drained
@@ -152,7 +166,8 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs_fast(const
                 if (ti + 1 < ntiles) {                    // table loads of the next tile first (L2 hits) ...
                     if (ti + 1 < nfull) load_feat(fr, r0 + 32, std::false_type{}); else load_feat(fr, r0 + 32, std::true_type{});
                 }
-                if (ti + RA < ntiles) load_ring(rr, r0 + 32 * RA);   // ... then the DRAM-latency ring loads, RA tiles ahead
+                if (RING2) __syncwarp();                  // keeps the ring loads behind the table loads in issue order
+                if (ti + RA < ntiles) load_ring(rr, r0 + 32 * RA);   // ... then the DRAM-latency ring loads
                 fence_proxy_async_smem();
                 __syncthreads();
                 const int nr = min(32, R - r0);
@@ -166,14 +181,11 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs_fast(const
                 buf ^= 1;
             };
             FeatRegs fr;
-            RingRegs rrA, rrB;
+            RingRegs rrA;
             if (nfull > 0) load_feat(fr, 0, std::false_type{}); else load_feat(fr, 0, std::true_type{});
+            if (RING2) __syncwarp();
             load_ring(rrA, 0);
-            if (RING2 && ntiles > 1) load_ring(rrB, 32);
-            for (int ti = 0; ti < ntiles; ti += RA) {
-                emit(fr, rrA, ti);
-                if (RING2 && ti + 1 < ntiles) emit(fr, rrB, ti + 1);
-            }
+            for (int ti = 0; ti < ntiles; ++ti) emit(fr, rrA, ti);
         }
     }
     if (tid == 0) bulk_wait_read<0>();
