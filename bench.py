@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (launch-bound small batches)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VAL",
                     help="kernel launch-shape override: rows|group|ctas|fused|fast = int (pmrl_set_tuning)")
     args = ap.parse_args()
@@ -205,8 +206,15 @@ def main():
     for i in range(preroll):
         env.step(pool[i % n_pool], obs=False)
 
-    def one_step(i):
-        env.step(pool[i % n_pool], obs=obs)
+    if args.graph:
+        static_actions, replay = env.graphed_step(obs=obs)
+
+        def one_step(i):
+            static_actions.copy_(pool[i % n_pool])         # the policy would write its actions here
+            replay()
+    else:
+        def one_step(i):
+            env.step(pool[i % n_pool], obs=obs)
 
     def barrier():
         if world > 1:
@@ -279,7 +287,7 @@ def main():
             "env_steps_per_s": value / A,
             "config": {"workload": args.workload, "description": desc, "envs_per_gpu": E, "envs_total": world * E,
                        "assets": A, "window": W, "features": F, "commission": commission, "obs_materialised": obs,
-                       "episode_len": EPISODE_LEN, "table_rows": TABLE_ROWS, "preroll_steps": preroll, "tune": args.tune, "actions": "raw N(0,1) scores (softmax branch)",
+                       "episode_len": EPISODE_LEN, "table_rows": TABLE_ROWS, "preroll_steps": preroll, "tune": args.tune, "cuda_graph": bool(args.graph), "actions": "raw N(0,1) scores (softmax branch)",
                        "parallelism": f"env-shard x{world}, NCCL stats all-reduce",
                        "l2_policy": "working set per step (obs write + ring) exceeds L2 (126 MB)" if E * A * W * 4 > 126e6
                                     else "working set smaller than L2: L2-resident by construction"},

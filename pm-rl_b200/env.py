@@ -96,14 +96,14 @@ class BatchedTradingEnv:
             self.t0 = torch.as_tensor(t0).to(device=dev, dtype=torch.int32).contiguous()
             if self.t0.shape != (E,):
                 raise ValueError(f"t0 must be [{E}]")
+        if W < 2:
+            raise ValueError("window_size must be >= 2 (the reference ring indexes row 1 on reset, weight_buffer.py:9-10)")
         if self.T:
             need = int(self.t0.max().item()) + cfg.episode_len + W if E else 0
             if need > self.T:
                 raise ValueError(f"table too short: max(t0) + episode_len + W = {need} > T = {self.T}")
             if E and int(self.t0.min().item()) < 0:
                 raise ValueError("t0 must be >= 0")
-            if W < 2 and E and int(self.t0.min().item()) < 1:
-                raise ValueError("W == 1 needs t0 >= 1 (y needs the previous close)")
         # ---- state ----
         self.value = torch.empty(E, dtype=torch.float32, device=dev)
         self.hist = torch.empty(E, W, A, dtype=torch.float32, device=dev)
@@ -173,6 +173,37 @@ class BatchedTradingEnv:
                                     _lib.current_stream())
         _lib.check(rc, "pmrl_env_step")
         return buf, self.reward, self.done
+
+    def graphed_step(self, obs: bool = True, out=None):
+        """Capture one step in a CUDA graph (launch-bound small batches: 4,096 x 50 moves 1.7 MB per state-only step).
+        Returns (static_actions [E, A], replay) — fill `static_actions` in place, then call `replay()` which
+        returns the same (obs, reward, done) buffers as `step`.  The kernels take no host-side decisions after
+        validation, so the captured launch is valid for every later step (auto-resets included)."""
+        static_actions = torch.zeros(self.E, self.A, dtype=torch.float32, device=self.device)
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):                        # warm-up launch outside capture (lazy module loading, smem attributes)
+            snap = [t.clone() for t in (self.value, self.hist, self.idx, self.is_full, self.t, self.ep_return)]
+            stats_snap = self._stats.clone() if self._stats is not None else None
+            self.step(static_actions, obs=obs, out=out)
+            for dst, src in zip((self.value, self.hist, self.idx, self.is_full, self.t, self.ep_return), snap):
+                dst.copy_(src)                            # undo the warm-up transition
+            if stats_snap is not None:
+                self._stats.copy_(stats_snap)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            result = self.step(static_actions, obs=obs, out=out)
+        for dst, src in zip((self.value, self.hist, self.idx, self.is_full, self.t, self.ep_return), snap):
+            dst.copy_(src)                                # capture does not execute, but keep the state explicit
+        if stats_snap is not None:
+            self._stats.copy_(stats_snap)
+
+        def replay():
+            g.replay()
+            return result
+
+        return static_actions, replay
 
     def write_weight_channel(self, obs):
         """features[:, :, -1] = weights.get_all() on a caller-filled obs [E, A, W, F] (trading_env.py:103)."""

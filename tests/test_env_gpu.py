@@ -292,3 +292,64 @@ def test_bad_arguments_raise():
     env = Env(pmrl.EnvConfig(num_envs=2, num_assets=5, window_size=8, episode_len=0))
     with pytest.raises(PmrlError):
         env.step(torch.zeros(2, 5, device="cuda"))                                                    # no table, no y
+
+
+def test_nan_inf_and_overflow_propagate_like_the_reference():
+    """No asserts / clamps on device: NaN, Inf and exp overflow flow through exactly like the torch reference ops."""
+    E, A, W, L = 12, 9, 4, 40
+    gpu, ora = make_pair(E, A, W, 5, episode_len=L)
+    g = torch.Generator().manual_seed(10)
+    act = torch.randn(E, A, generator=g)
+    act[0, 3] = float("nan")          # NaN score: sum is NaN, min is NaN -> no normalisation -> NaN value
+    act[1, :] = 100.0; act[1, 0] = -1.0   # exp(100) overflows fp32: inf / inf = NaN weights (quirk Q3)
+    act[2, 2] = float("inf"); act[2, 0] = -1.0
+    act[3] = torch.softmax(act[3], 0)     # well-behaved rows stay finite
+    _, r, _ = gpu.step(act.cuda(), obs=False)
+    with np.errstate(all="ignore"):
+        r_o, _ = ora.step(act.numpy())
+    got_v, want_v = gpu.value.cpu().numpy(), ora.value
+    np.testing.assert_array_equal(np.isnan(got_v), np.isnan(want_v))
+    np.testing.assert_array_equal(np.isnan(r.cpu().numpy()), np.isnan(r_o))
+    assert np.isnan(want_v[:3]).all() and np.isfinite(want_v[3:]).all()
+    ok = np.isfinite(want_v)
+    util.assert_values_close(got_v[ok], want_v[ok])
+
+
+@pytest.mark.parametrize("A", [129, 513, 1024])
+def test_wide_asset_counts(A, tuning):
+    """A up to 1024 (32 assets per lane); state-only and fused generic paths."""
+    E, W, L = 10, 6, 12
+    gpu, ora = make_pair(E, A, W, 5, episode_len=L)
+    g = torch.Generator().manual_seed(A)
+    obs = gpu.reset()
+    for s in range(L + 2):
+        act = torch.randn(E, A, generator=g)
+        obs, r, done = gpu.step(act.cuda(), obs=(s % 2 == 0))
+        r_o, d_o = ora.step(act.numpy())
+        util.assert_rewards_close(r.cpu().numpy(), r_o, f"step {s}")
+        np.testing.assert_array_equal(done.cpu().numpy(), d_o)
+    compare_state(gpu, ora, "end")
+    compare_obs(gpu.observe(), ora, "end")
+
+
+def test_graphed_step_matches_eager():
+    E, A, W, L = 64, 20, 8, 25
+    gpu, ora = make_pair(E, A, W, 5, episode_len=L)
+    gpu.reset()
+    static_actions, replay = gpu.graphed_step(obs=True)
+    g = torch.Generator().manual_seed(3)
+    for s in range(2 * L + 3):
+        act = torch.randn(E, A, generator=g)
+        static_actions.copy_(act)
+        obs, r, done = replay()
+        r_o, d_o = ora.step(act.numpy())
+        util.assert_rewards_close(r.cpu().numpy(), r_o, f"step {s}")
+        np.testing.assert_array_equal(done.cpu().numpy(), d_o)
+    compare_state(gpu, ora, "end")
+    compare_obs(obs, ora, "end")
+
+
+def test_window_of_one_is_rejected_like_the_reference_would_fail():
+    pmrl, synth, Env = _mods()
+    with pytest.raises(ValueError):
+        Env(pmrl.EnvConfig(num_envs=2, num_assets=3, window_size=1, episode_len=0))
