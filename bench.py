@@ -178,7 +178,7 @@ def main():
     rank, world, local_rank = pdist.init_from_env()
     from pmrl_b200 import _lib
     tune_keys = {"rows": _lib.TUNE_TILE_ROWS, "group": _lib.TUNE_GROUP_ENVS, "ctas": _lib.TUNE_CTAS_PER_SM,
-                 "fused": _lib.TUNE_FUSED, "fast": _lib.TUNE_FAST_FILL, "tma": _lib.TUNE_TMA_PIPELINE, "stages": _lib.TUNE_TMA_STAGES, "var": _lib.TUNE_FAST_VARIANT}
+                 "fused": _lib.TUNE_FUSED, "fast": _lib.TUNE_FAST_FILL, "tma": _lib.TUNE_TMA_PIPELINE, "stages": _lib.TUNE_TMA_STAGES, "var": _lib.TUNE_FAST_VARIANT, "rt": _lib.TUNE_RING_TMA}
     for kv in args.tune:
         k, v = kv.split("=")
         _lib.set_tuning(tune_keys[k], int(v))
@@ -294,7 +294,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak,
                          "traffic": ncu_traffic_bytes(args.workload), "algorithmic_bytes_per_launch": bpa * E * A,
                          "bytes_per_asset_step": bpa, "peak_source": peak_src,
-                         "kernel": "k_env_step_obs_fast" if obs else "k_env_step"},
+                         "kernel": "k_env_step_obs_rt" if obs else "k_env_step"},
             "clocks": clocks,
             "gpu_launches": launches_per_step * args.steps,
             "stats": {k: stats[k] for k in ("n_envs", "mean_reward", "mean_value", "n_done")},

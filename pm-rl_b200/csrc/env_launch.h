@@ -10,3 +10,6 @@ int pmrl_launch_step_obs_tma(pmrl::StepParams& p, int npl, int stages, int group
 // Register-staged fused step+obs kernel (env_step_fast.cu).  Returns -100 if the shape is not covered.
 int pmrl_launch_step_obs_fast(pmrl::StepParams& p, int npl, int group, int ctas_per_sm, cudaStream_t s);
 void pmrl_set_fast_variant(int v);
+
+// Variant of the fused kernel that brings each env's weight ring in with one TMA bulk load (env_step_rt.cu).
+int pmrl_launch_step_obs_rt(pmrl::StepParams& p, int npl, int group, int ctas_per_sm, cudaStream_t s);

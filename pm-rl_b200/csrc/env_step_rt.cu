@@ -1,0 +1,224 @@
+// env_step_rt.cu — fused step + observation kernel, variant "RT": the weight ring of an env enters the SM as ONE
+// contiguous TMA bulk load (W·A·4 bytes, e.g. 20 KB) instead of 8 register loads per thread and tile.
+//
+// Same structure as env_step_fast.cu (persistent CTAs, groups of G <= 8 envs, 32-asset-row tiles, register-staged
+// table loads, one TMA bulk store per tile) with these differences:
+//   * ring rows never travel through registers or the L1 load queue: thread 0 issues cp.async.bulk global→shared for
+//     the whole ring of env el (double-buffered: envs el and el+1 resident), completion on an mbarrier; the weight
+//     channel of a tile is then filled from shared memory (lanes over assets: conflict-free).  The L1 queue only
+//     carries the L2-hit table loads, so no DRAM-latency load can sit in front of them, and DRAM sees one
+//     page-friendly 20 KB read per env instead of 200 scattered 128-byte reads;
+//   * 2 CTAs per SM (110 KB of shared memory each), up to 128 registers, no spills.
+// Requires (W·A) % 4 == 0 (16-byte alignment of every env's ring) and 2·W·A·4 + tiles to fit in shared memory.
+// Weight channel semantics: ActionBuffer.get_all (weight_buffer.py:32-44), fresh row from shared memory.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <type_traits>
+#include "pmrl_b200.h"
+#include "pmrl_device.cuh"
+#include "env_step.cuh"
+#include "env_launch.h"
+#include "host_util.h"
+
+namespace pmrl {
+
+constexpr int kRtThreads = 256;
+constexpr int kRtWarps = kRtThreads / 32;
+constexpr int kRtGroup = kRtWarps;
+
+struct RtEnv { int row0, shift, fresh_slot, pad; };
+struct RtFeat { float4 fv[4][2]; };
+
+template <int NPL, bool HASC, int WT>
+__global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double s_stats[kRtWarps * PMRL_STATS_LEN];
+    __shared__ RtEnv s_env[kRtGroup];
+    __shared__ __align__(8) uint64_t s_rbar[2];
+    const int W = WT ? WT : p.W;
+    const int A = p.A, T = p.T, G = p.group_envs;
+    const int WA = W * A;
+    const int tile_floats = 32 * W * 5;
+    float* const tile0 = reinterpret_cast<float*>(smem_raw);
+    float* const tile1 = tile0 + tile_floats;
+    float* const s_ring = tile1 + tile_floats;                       // [2][W*A] rings of two consecutive envs
+    float* const s_wnew = s_ring + 2 * WA;                           // [G*A]    w' per asset-row of the group
+    int* const s_ea = reinterpret_cast<int*>(s_wnew + G * A);        // [G*A]    (env-in-group << 16) | asset
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_groups = (p.E + G - 1) / G;
+    const size_t row_floats = (size_t)W * 5;
+    if (tid == 0) { mbar_init(&s_rbar[0], 1); mbar_init(&s_rbar[1], 1); mbar_fence_init(); }
+    if (p.stats) stats_init_block(s_stats, kRtWarps); else __syncthreads();
+
+    const int fbase = (warp * W + lane) * 5, fstep = 8 * W * 5;
+    const bool w0 = lane < W, w1 = lane + 32 < W;
+    const int wbase = (lane * W + warp) * 5 + 4;
+    const int nj = min(8, max(0, (W - warp + 7) >> 3));
+    const float4* __restrict__ tbl = reinterpret_cast<const float4*>(p.feat_am) + lane;
+
+    int buf = 0;
+    int ebase = 0;                                                   // envs streamed by this CTA so far (ring buffer / phase index)
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int e0 = grp * G;
+        const int ne = min(G, p.E - e0);
+        // ---------------- phase 1: one warp per env ----------------
+        if (warp < ne) {
+            const int e = e0 + warp;
+            EnvVectors<NPL, HASC> ev;
+            StepOut so;
+            env_step_warp<NPL, HASC>(p, e, lane, ev, so, s_stats + warp * PMRL_STATS_LEN);
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) {
+                const int a = lane + 32 * j;
+                if (a < A) { s_wnew[warp * A + a] = ev.a[j]; s_ea[warp * A + a] = (warp << 16) | a; }
+            }
+            if (lane == 0) {
+                RtEnv ge;
+                ge.row0 = p.t0[e] + so.k;
+                ge.shift = so.is_full ? 0 : (W - so.idx_new);          // weight_buffer.py:38-42
+                ge.fresh_slot = so.did_reset ? 0 : so.slot_written;     // the row written by this launch comes from smem
+                ge.pad = 0;
+                s_env[warp] = ge;
+            }
+        }
+        __syncthreads();
+        // ---------------- phase 2 ----------------
+        const int R = ne * A;
+        const int ntiles = (R + 31) >> 5, nfull = R >> 5;
+        const float* __restrict__ hist_g = p.hist + (size_t)e0 * WA;
+        float* const obs_grp = p.obs + (size_t)e0 * A * row_floats;
+        int issued = 0;                                               // envs of this group whose ring load has been issued
+        auto issue_rings = [&](int upto) {                            // thread 0 only
+            for (; issued < upto; ++issued) {
+                const int n = ebase + issued;
+                mbar_arrive_expect_tx(&s_rbar[n & 1], (uint32_t)WA * 4u);
+                bulk_load_g2s(s_ring + (n & 1) * WA, hist_g + (size_t)issued * WA, (uint32_t)WA * 4u, &s_rbar[n & 1], kPolicyEvictFirst);
+            }
+        };
+        if (tid == 0) issue_rings(min(ne, 2));
+        int wel = lane / A, wa = lane - wel * A;                      // (env-in-group, asset) of this lane's weight row
+
+        auto load_feat = [&](RtFeat& fr, int r0, auto partial) {
+            constexpr bool PARTIAL = decltype(partial)::value;
+            const int nr = PARTIAL ? R - r0 : 32;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!PARTIAL || warp + 8 * i < nr) {
+                    const int ea = s_ea[r0 + warp + 8 * i];
+                    const float4* __restrict__ src = tbl + ((ea & 0xffff) * T + s_env[ea >> 16].row0);
+                    if (w0) fr.fv[i][0] = ld_keep4(src, kPolicyEvictLast);
+                    if (w1) fr.fv[i][1] = ld_keep4(src + 32, kPolicyEvictLast);
+                }
+            }
+        };
+        auto spill_tile = [&](const RtFeat& fr, float* __restrict__ tile, int r0, auto partial) {
+            constexpr bool PARTIAL = decltype(partial)::value;
+            const int nr = PARTIAL ? R - r0 : 32;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!PARTIAL || warp + 8 * i < nr) {
+                    float* d = tile + fbase + i * fstep;
+                    if (w0) { const float4 v = fr.fv[i][0]; d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+                    if (w1) { const float4 v = fr.fv[i][1]; d[160] = v.x; d[161] = v.y; d[162] = v.z; d[163] = v.w; }
+                }
+            }
+            if (!PARTIAL || lane < nr) {                              // weight channel straight from the staged ring
+                const int n = ebase + wel;
+                mbar_wait(&s_rbar[n & 1], (uint32_t)((n >> 1) & 1));
+                const RtEnv ge = s_env[wel];
+                const float* __restrict__ rs = s_ring + (n & 1) * WA + wa;
+                const float fresh = s_wnew[r0 + lane];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < nj) {
+                        const int slot = warp + 8 * j - ge.shift;
+                        float v = 0.0f;                               // zero front padding while the ring is not full
+                        if (slot >= 0) v = (slot == ge.fresh_slot) ? fresh : rs[slot * A];
+                        tile[wbase + 40 * j] = v;
+                    }
+                }
+            }
+            wa += 32;
+            while (wa >= A) { wa -= A; ++wel; }
+        };
+
+        RtFeat fr;
+        if (nfull > 0) load_feat(fr, 0, std::false_type{}); else load_feat(fr, 0, std::true_type{});
+        for (int ti = 0; ti < ntiles; ++ti) {
+            float* const tile = buf ? tile1 : tile0;
+            if (tid == 0) bulk_wait_read<1>();                        // the store that last used this buffer has drained
+            __syncthreads();
+            const int r0 = ti * 32;
+            if (ti < nfull) spill_tile(fr, tile, r0, std::false_type{}); else spill_tile(fr, tile, r0, std::true_type{});
+            if (ti + 1 < ntiles) {
+                if (ti + 1 < nfull) load_feat(fr, r0 + 32, std::false_type{}); else load_feat(fr, r0 + 32, std::true_type{});
+            }
+            fence_proxy_async_smem();
+            __syncthreads();
+            const int nr = min(32, R - r0);
+            float* const gdst = obs_grp + (size_t)r0 * row_floats;
+            const int n = nr * W * 5;
+            if (((((uintptr_t)gdst) | ((size_t)n * 4)) & 15) == 0) {
+                if (tid == 0) { bulk_store_s2g(gdst, tile, (uint32_t)n * 4u, kPolicyEvictFirst); bulk_commit(); }
+            } else {
+                for (int q = tid; q < n; q += kRtThreads) gdst[q] = tile[q];
+            }
+            // envs below (r0+32)/A are complete (every thread passed the barrier after its last read of their ring):
+            // their buffers can take the rings of the envs two positions further on
+            if (tid == 0) issue_rings(min(ne, (r0 + 32) / A + 2));
+            buf ^= 1;
+        }
+        ebase += ne;
+    }
+    if (tid == 0) bulk_wait_read<0>();
+    if (p.stats) stats_flush_block(p.stats, s_stats, kRtWarps);
+}
+
+}  // namespace pmrl
+
+using namespace pmrl;
+
+template <int NPL, bool HASC, int WT>
+static int launch_rt_t(StepParams& p, size_t smem, int grid, cudaStream_t s) {
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs_rt<NPL, HASC, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (e != cudaSuccess) return pmrl_fail((int)e, "cudaFuncSetAttribute(k_env_step_obs_rt) failed");
+        attr_done[dev] = true;
+    }
+    k_env_step_obs_rt<NPL, HASC, WT><<<grid, kRtThreads, smem, s>>>(p);
+    return pmrl_check_launch("k_env_step_obs_rt");
+}
+
+template <int NPL, bool HASC>
+static int launch_rt_w(StepParams& p, size_t smem, int grid, cudaStream_t s) {
+    if (p.W == 50) return launch_rt_t<NPL, HASC, 50>(p, smem, grid, s);
+    return launch_rt_t<NPL, HASC, 0>(p, smem, grid, s);
+}
+
+int pmrl_launch_step_obs_rt(StepParams& p, int npl, int group, int ctas_per_sm, cudaStream_t s) {
+    if (p.F != 5 || p.W > 64 || npl > 4 || p.A < 32) return -100;     // A >= 32: a 32-row tile spans at most two envs
+    if (((size_t)p.W * p.A) % 4 != 0 || ((uintptr_t)p.hist) % 16 != 0) return -100;   // every env's ring 16-byte aligned
+    if ((size_t)p.A * p.T >= (1u << 31) || p.A >= 65536) return -100;
+    const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : 2;
+    const int slots = pmrl_sm_count() * per_sm;
+    int G = group > 0 ? group : kRtGroup;
+    if (G > kRtGroup) G = kRtGroup;
+    while (G > 1 && (p.E + G - 1) / G < 2 * slots) G >>= 1;
+    p.group_envs = G;
+    p.tile_assets = 32;
+    const size_t smem = (size_t)2 * 32 * p.W * 5 * 4 + (size_t)2 * p.W * p.A * 4 + (size_t)G * p.A * 8;
+    if (smem > (size_t)(226 * 1024) / per_sm - 1024) return -100;
+    const int n_groups = (p.E + G - 1) / G;
+    const int grid = n_groups < slots ? n_groups : slots;
+    const bool hasc = p.commission > 0.0f;
+#define RT_CASE(N) return hasc ? launch_rt_w<N, true>(p, smem, grid, s) : launch_rt_w<N, false>(p, smem, grid, s)
+    switch (npl) {
+        case 1: RT_CASE(1);
+        case 2: RT_CASE(2);
+        default: RT_CASE(4);
+    }
+#undef RT_CASE
+}

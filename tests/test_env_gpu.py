@@ -98,14 +98,16 @@ def tuning():
         _lib.set_tuning(k, 0)
     _lib.set_tuning(_lib.TUNE_FUSED, 1)
     _lib.set_tuning(_lib.TUNE_TMA_PIPELINE, DEFAULT_TMA)
+    _lib.set_tuning(_lib.TUNE_RING_TMA, 1)
     _lib.set_tuning(_lib.TUNE_FAST_FILL, 1)
 
 
 DEFAULT_TMA = 0
 # (fused, tile_rows, group_envs, tma, stages | fast): the fused step+obs kernel in several launch shapes (register-staged
-# fast fill, generic fill, warp-specialised TMA pipeline with 2..6 stages) and the two-kernel path
+# fast fill, generic fill, warp-specialised TMA pipeline with 2..6 stages (tma=1), ring-through-TMA variant (tma=2))
+# and the two-kernel path
 VARIANTS = [(1, 0, 0, 0, 1), (1, 0, 3, 0, 1), (1, 8, 3, 0, 0), (1, 32, 1, 0, 0), (0, 0, 0, 0, 1),
-            (1, 0, 0, 1, 4), (1, 0, 2, 1, 2), (1, 0, 8, 1, 6)]
+            (1, 0, 0, 1, 4), (1, 0, 2, 1, 2), (1, 0, 8, 1, 6), (1, 0, 0, 2, 1), (1, 0, 3, 2, 1)]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -117,8 +119,9 @@ def test_table_driven_step_and_obs_vs_oracle(A, W, F, E, variant, tuning):
     tuning.set_tuning(tuning.TUNE_FUSED, fused)
     tuning.set_tuning(tuning.TUNE_TILE_ROWS, rows)
     tuning.set_tuning(tuning.TUNE_GROUP_ENVS, group)
-    tuning.set_tuning(tuning.TUNE_TMA_PIPELINE, tma)
-    if tma:
+    tuning.set_tuning(tuning.TUNE_TMA_PIPELINE, 1 if tma == 1 else 0)
+    tuning.set_tuning(tuning.TUNE_RING_TMA, 1 if tma == 2 else 0)
+    if tma == 1:
         tuning.set_tuning(tuning.TUNE_TMA_STAGES, depth)
     else:
         tuning.set_tuning(tuning.TUNE_FAST_FILL, depth)
