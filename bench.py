@@ -246,16 +246,13 @@ def main():
     e2e = None
     if not args.no_e2e:
         h_act = [p.cpu().pin_memory() for p in pool[:2]]
-        d_act = torch.empty(E, A, device=dev)
         h_rew = torch.empty(E, dtype=torch.float32).pin_memory()
         h_done = torch.empty(E, dtype=torch.uint8).pin_memory()
 
         def e2e_step(i):
-            d_act.copy_(h_act[i % 2], non_blocking=True)
-            _, r, d = env.step(d_act, obs=obs)
-            h_rew.copy_(r, non_blocking=True)
-            h_done.copy_(d, non_blocking=True)
-            torch.cuda.current_stream().synchronize()          # the caller reads the reward before acting again
+            # public host-buffer API: pinned actions in, reward/done out, the caller blocks until they are on the host.
+            # Internally the batch is issued as 4 env slices so the H2D copy of slice c+1 overlaps the kernel of slice c.
+            env.step_host(h_act[i % 2], h_rew, h_done, obs=obs)
 
         for i in range(3):
             e2e_step(i)

@@ -356,3 +356,22 @@ def test_window_of_one_is_rejected_like_the_reference_would_fail():
     pmrl, synth, Env = _mods()
     with pytest.raises(ValueError):
         Env(pmrl.EnvConfig(num_envs=2, num_assets=3, window_size=1, episode_len=0))
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 4])
+def test_step_host_chunked_matches_step(chunks):
+    """Host-buffer step (H2D of slice c+1 overlapping the kernel of slice c) gives the same transition as step()."""
+    E, A, W, L = 50, 40, 8, 30
+    gpu, ora = make_pair(E, A, W, 5, episode_len=L, collect_stats=True)
+    gpu.reset()
+    g = torch.Generator().manual_seed(11)
+    h_r = torch.empty(E, dtype=torch.float32).pin_memory(); h_d = torch.empty(E, dtype=torch.uint8).pin_memory()
+    for s in range(L + 4):
+        act = torch.randn(E, A, generator=g).pin_memory()
+        obs, r, d = gpu.step_host(act, h_r, h_d, chunks=chunks)
+        r_o, d_o = ora.step(act.numpy())
+        util.assert_rewards_close(r.numpy(), r_o, f"step {s}")
+        np.testing.assert_array_equal(d.numpy(), d_o)
+    compare_state(gpu, ora, "end")
+    compare_obs(obs, ora, "end")
+    assert gpu.stats()["n_envs"] == E * (L + 4) - E      # one auto-reset call per env is not a step
