@@ -178,7 +178,7 @@ def main():
     rank, world, local_rank = pdist.init_from_env()
     from pmrl_b200 import _lib
     tune_keys = {"rows": _lib.TUNE_TILE_ROWS, "group": _lib.TUNE_GROUP_ENVS, "ctas": _lib.TUNE_CTAS_PER_SM,
-                 "fused": _lib.TUNE_FUSED, "fast": _lib.TUNE_FAST_FILL, "tma": _lib.TUNE_TMA_PIPELINE, "stages": _lib.TUNE_TMA_STAGES, "var": _lib.TUNE_FAST_VARIANT, "rt": _lib.TUNE_RING_TMA}
+                 "fused": _lib.TUNE_FUSED, "fast": _lib.TUNE_FAST_FILL, "tma": _lib.TUNE_TMA_PIPELINE, "stages": _lib.TUNE_TMA_STAGES, "var": _lib.TUNE_FAST_VARIANT, "rt": _lib.TUNE_RING_TMA, "tm": _lib.TUNE_TENSORMAP}
     for kv in args.tune:
         k, v = kv.split("=")
         _lib.set_tuning(tune_keys[k], int(v))

@@ -126,6 +126,7 @@ const char* pmrl_last_error(void);
 #define PMRL_TUNE_TMA_PIPELINE 8  /* 1: warp-specialised TMA-load pipeline variant of the fused kernel (F == 5, W <= 64, A <= 512) */
 #define PMRL_TUNE_TMA_STAGES  9   /* staging buffers of that variant (2..6) */
 #define PMRL_TUNE_RING_TMA    11  /* 1 (default): fused kernel that loads each env's weight ring with one TMA bulk copy (env_step_rt.cu); 0: register ring loads (env_step_fast.cu) */
+#define PMRL_TUNE_TENSORMAP   12  /* 1: fused kernel variant whose feature windows arrive as tensor-map TMA boxes (env_step_tm.cu) */
 #define PMRL_TUNE_FAST_VARIANT 10 /* code-generation variant mask of the register-staged kernel (A/B measurement; see env_step_fast.cu) */
 int pmrl_set_tuning(int32_t key, int32_t value);
 

@@ -113,7 +113,7 @@ def current_stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-TUNE_TILE_ROWS, TUNE_GROUP_ENVS, TUNE_CTAS_PER_SM, TUNE_FUSED, TUNE_FAST_FILL, TUNE_TMA_PIPELINE, TUNE_TMA_STAGES, TUNE_FAST_VARIANT, TUNE_RING_TMA = 1, 2, 3, 4, 5, 8, 9, 10, 11
+TUNE_TILE_ROWS, TUNE_GROUP_ENVS, TUNE_CTAS_PER_SM, TUNE_FUSED, TUNE_FAST_FILL, TUNE_TMA_PIPELINE, TUNE_TMA_STAGES, TUNE_FAST_VARIANT, TUNE_RING_TMA, TUNE_TENSORMAP = 1, 2, 3, 4, 5, 8, 9, 10, 11, 12
 
 
 def set_tuning(key: int, value: int) -> None:

@@ -339,7 +339,7 @@ static int launch_step_npl(const StepParams& p, int npl, cudaStream_t s) {
 }
 
 // Fused Mode-O launch: tile rows, group size and grid from the shape (tunable through pmrl_set_tuning).
-static int g_tune_rows = 0, g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1, g_tune_fast = 1, g_tune_tma = 0, g_tune_stages = 0, g_tune_rt = 1;
+static int g_tune_rows = 0, g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1, g_tune_fast = 1, g_tune_tma = 0, g_tune_stages = 0, g_tune_rt = 1, g_tune_tm = 0;
 
 extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
     switch (key) {
@@ -352,6 +352,7 @@ extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
         case PMRL_TUNE_TMA_STAGES: g_tune_stages = value; return 0;
         case PMRL_TUNE_FAST_VARIANT: pmrl_set_fast_variant(value); return 0;
         case PMRL_TUNE_RING_TMA: g_tune_rt = value; return 0;
+        case PMRL_TUNE_TENSORMAP: g_tune_tm = value; return 0;
         default: return pmrl_fail(PMRL_E_ARG, "unknown tuning key");
     }
 }
@@ -387,6 +388,10 @@ static int launch_fused(StepParams& p, float* obs, int npl, cudaStream_t s) {
     if (g_tune_fast && g_tune_tma) {                  // warp-specialised TMA pipeline (env_step_tma.cu)
         const int rc = pmrl_launch_step_obs_tma(p, npl, g_tune_stages, g_tune_group, s);
         if (rc != -100) return rc;                    // -100: shape not covered by that variant → fall through
+    }
+    if (g_tune_fast && g_tune_tm) {                   // all loads through TMA: tensor-map feature boxes + ring bulk loads (env_step_tm.cu)
+        const int rc = pmrl_launch_step_obs_tm(p, npl, g_tune_group, g_tune_ctas_per_sm, s);
+        if (rc != -100) return rc;
     }
     if (g_tune_fast && g_tune_rt) {                   // ring rows through one TMA bulk load per env (env_step_rt.cu)
         const int rc = pmrl_launch_step_obs_rt(p, npl, g_tune_group, g_tune_ctas_per_sm, s);

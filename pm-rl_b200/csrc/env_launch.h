@@ -13,3 +13,6 @@ void pmrl_set_fast_variant(int v);
 
 // Variant of the fused kernel that brings each env's weight ring in with one TMA bulk load (env_step_rt.cu).
 int pmrl_launch_step_obs_rt(pmrl::StepParams& p, int npl, int group, int ctas_per_sm, cudaStream_t s);
+
+// Variant with tensor-map TMA loads of the feature windows (env_step_tm.cu).
+int pmrl_launch_step_obs_tm(pmrl::StepParams& p, int npl, int group, int ctas_per_sm, cudaStream_t s);

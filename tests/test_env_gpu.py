@@ -99,19 +99,21 @@ def tuning():
     _lib.set_tuning(_lib.TUNE_FUSED, 1)
     _lib.set_tuning(_lib.TUNE_TMA_PIPELINE, DEFAULT_TMA)
     _lib.set_tuning(_lib.TUNE_RING_TMA, 1)
+    _lib.set_tuning(_lib.TUNE_TENSORMAP, DEFAULT_TM)
     _lib.set_tuning(_lib.TUNE_FAST_FILL, 1)
 
 
 DEFAULT_TMA = 0
+DEFAULT_TM = 0
 # (fused, tile_rows, group_envs, tma, stages | fast): the fused step+obs kernel in several launch shapes (register-staged
-# fast fill, generic fill, warp-specialised TMA pipeline with 2..6 stages (tma=1), ring-through-TMA variant (tma=2))
+# fast fill, generic fill, warp-specialised TMA pipeline with 2..6 stages (tma=1), ring-through-TMA variant (tma=2), tensor-map TMA variant (tma=3))
 # and the two-kernel path
 VARIANTS = [(1, 0, 0, 0, 1), (1, 0, 3, 0, 1), (1, 8, 3, 0, 0), (1, 32, 1, 0, 0), (0, 0, 0, 0, 1),
-            (1, 0, 0, 1, 4), (1, 0, 2, 1, 2), (1, 0, 8, 1, 6), (1, 0, 0, 2, 1), (1, 0, 3, 2, 1)]
+            (1, 0, 0, 1, 4), (1, 0, 2, 1, 2), (1, 0, 8, 1, 6), (1, 0, 0, 2, 1), (1, 0, 3, 2, 1), (1, 0, 0, 3, 1), (1, 0, 3, 3, 1)]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
-@pytest.mark.parametrize("A,W,F,E", [(11, 50, 5, 48), (50, 50, 5, 48), (100, 50, 5, 45), (500, 50, 5, 21), (7, 5, 3, 50),
+@pytest.mark.parametrize("A,W,F,E", [(11, 50, 5, 48), (50, 50, 5, 48), (100, 50, 5, 45), (64, 24, 5, 37), (500, 50, 5, 21), (7, 5, 3, 50),
                                      (33, 9, 6, 48), (130, 16, 2, 40), (1, 4, 5, 9), (3, 300, 5, 5)])
 def test_table_driven_step_and_obs_vs_oracle(A, W, F, E, variant, tuning):
     """Batched, table-driven: window gather, y from the close plane, ring wrap, done and auto-reset."""
@@ -121,6 +123,7 @@ def test_table_driven_step_and_obs_vs_oracle(A, W, F, E, variant, tuning):
     tuning.set_tuning(tuning.TUNE_GROUP_ENVS, group)
     tuning.set_tuning(tuning.TUNE_TMA_PIPELINE, 1 if tma == 1 else 0)
     tuning.set_tuning(tuning.TUNE_RING_TMA, 1 if tma == 2 else 0)
+    tuning.set_tuning(tuning.TUNE_TENSORMAP, 1 if tma == 3 else 0)
     if tma == 1:
         tuning.set_tuning(tuning.TUNE_TMA_STAGES, depth)
     else:
