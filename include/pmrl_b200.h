@@ -22,6 +22,7 @@
  *   pmrl_ffd_transform  <- FixedFracDiff.transform       data/ffd.py:80-89
  *   pmrl_scale_series   <- Instrument.scale              data/instrument.py:318-336
  *   pmrl_pack_features  <- Instrument.window / get_feature_tensor layout (instrument.py:339-356)
+ *   pmrl_indicators     <- Instrument.add_indicators (TA-Lib windows)     data/instrument.py:207-232, config/base.py:30-44
  *   pmrl_rollout_add    <- RolloutBuffer.add             replay/rollout_buffer.py:43-57
  *   pmrl_rollout_gather <- RolloutBuffer.sample[_random] replay/rollout_buffer.py:59-142
  *   pmrl_replay_add     <- ReplayBuffer.add              replay/buffer.py:23-37, replay/traj_buffer.py:26-43
@@ -177,6 +178,21 @@ int pmrl_scale_series(const float* x, int32_t N, int32_t L, int32_t method, floa
  *   series [A*C, L] (series index = a*C + c)  →  feat_am [A, L, C];  close [A, L] → close_tm [L, A]. */
 int pmrl_pack_features(const float* series, const float* close, int32_t A, int32_t C, int32_t L,
                        float* feat_am, float* close_tm, void* stream);
+
+/* Technical-indicator windows (data/instrument.py:207-232; TA-Lib's published algorithms in double precision, outputs
+ * fp32 with NaN over each indicator's lookback — TA-Lib is not vendored: parity UNPINNED).
+ * specs: HOST array [n_specs, 2] of (PMRL_IND_*, period); series [A*C, L] with channels o,h,l,c[,v] (index a*C + c);
+ * out [A, n_out, L] where n_out / the maximum lookback come from pmrl_indicator_layout (BBANDS: upper, middle, lower;
+ * MACD 12/26/9: macd, signal, hist; the others one output). */
+#define PMRL_IND_SMA    0
+#define PMRL_IND_EMA    1
+#define PMRL_IND_RSI    2
+#define PMRL_IND_ATR    3
+#define PMRL_IND_BBANDS 4
+#define PMRL_IND_MACD   5
+int pmrl_indicator_layout(const int32_t* specs, int32_t n_specs, int32_t* n_out, int32_t* lookback);
+int pmrl_indicators(const float* series, int32_t A, int32_t C, int32_t L, const int32_t* specs, int32_t n_specs,
+                    float* out, void* stream);
 
 /* ---- buffers (replay/rollout_buffer.py, replay/buffer.py, replay/traj_buffer.py) ---- */
 

@@ -1,0 +1,71 @@
+"""CPU oracle of the indicator windows — TEST INFRASTRUCTURE (see oracle/env_oracle.py header).
+
+The reference computes indicators with TA-Lib's abstract functions on float64 OHLCV (data/instrument.py:207-232).
+TA-Lib is neither vendored nor pinned (it is not even in requirements.txt) and is absent from this image → parity
+UNPINNED: these functions restate TA-Lib's published algorithms (SMA-seeded EMA, Wilder-smoothed RSI / ATR,
+population-std Bollinger bands, 12/26/9 MACD with both EMAs seeded at index 25) in float64, outputs float32 with NaN
+over the lookback, exactly the conventions `abstract.Function.run` has."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def sma(c, n):
+    c = np.asarray(c, np.float64); out = np.full(c.shape, np.nan)
+    cs = np.cumsum(np.insert(c, 0, 0.0))
+    out[n - 1:] = (cs[n:] - cs[:-n]) / n
+    return out.astype(np.float32)
+
+
+def ema(c, n):
+    c = np.asarray(c, np.float64); out = np.full(c.shape, np.nan); k = 2.0 / (n + 1.0)
+    e = c[:n].mean(); out[n - 1] = e
+    for t in range(n, len(c)):
+        e = (c[t] - e) * k + e; out[t] = e
+    return out.astype(np.float32)
+
+
+def rsi(c, n):
+    c = np.asarray(c, np.float64); out = np.full(c.shape, np.nan)
+    d = np.diff(c); g = np.maximum(d, 0); l = np.maximum(-d, 0)
+    ag, al = g[:n].mean(), l[:n].mean()
+    out[n] = 100 * ag / (ag + al) if ag + al != 0 else 0.0
+    for t in range(n + 1, len(c)):
+        ag = (ag * (n - 1) + g[t - 1]) / n; al = (al * (n - 1) + l[t - 1]) / n
+        out[t] = 100 * ag / (ag + al) if ag + al != 0 else 0.0
+    return out.astype(np.float32)
+
+
+def atr(h, l, c, n):
+    h, l, c = (np.asarray(x, np.float64) for x in (h, l, c)); out = np.full(c.shape, np.nan)
+    tr = np.maximum(h[1:] - l[1:], np.maximum(np.abs(h[1:] - c[:-1]), np.abs(l[1:] - c[:-1])))
+    a = tr[:n].mean(); out[n] = a
+    for t in range(n + 1, len(c)):
+        a = (a * (n - 1) + tr[t - 1]) / n; out[t] = a
+    return out.astype(np.float32)
+
+
+def bbands(c, n):
+    c = np.asarray(c, np.float64); up = np.full(c.shape, np.nan); mid = up.copy(); lo = up.copy()
+    for t in range(n - 1, len(c)):
+        w = c[t - n + 1:t + 1]; m = w.mean(); sd = np.sqrt(max((w * w).mean() - m * m, 0.0))
+        up[t], mid[t], lo[t] = m + 2 * sd, m, m - 2 * sd
+    return up.astype(np.float32), mid.astype(np.float32), lo.astype(np.float32)
+
+
+def macd(c):
+    c = np.asarray(c, np.float64); L = len(c)
+    m = np.full(L, np.nan); sg = m.copy(); hs = m.copy()
+    kf, ks, kg = 2 / 13.0, 2 / 27.0, 2 / 10.0
+    es, ef = c[:26].mean(), c[14:26].mean()
+    raw = [ef - es]
+    for t in range(26, L):
+        es = (c[t] - es) * ks + es; ef = (c[t] - ef) * kf + ef; raw.append(ef - es)
+    raw = np.array(raw)
+    eg = raw[:9].mean()
+    for q in range(8, len(raw)):
+        if q > 8:
+            eg = (raw[q] - eg) * kg + eg
+        t = q + 25
+        m[t], sg[t], hs[t] = raw[q], eg, raw[q] - eg
+    return m.astype(np.float32), sg.astype(np.float32), hs.astype(np.float32)

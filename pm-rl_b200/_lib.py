@@ -46,6 +46,8 @@ SIGNATURES = {
     "pmrl_ffd_transform": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, i32, i32, i32, c_void_p, c_void_p]),
     "pmrl_scale_series": (C.c_int, [c_void_p, i32, i32, i32, c_void_p, c_void_p]),
     "pmrl_pack_features": (C.c_int, [c_void_p, c_void_p, i32, i32, i32, c_void_p, c_void_p, c_void_p]),
+    "pmrl_indicator_layout": (C.c_int, [c_void_p, i32, c_void_p, c_void_p]),
+    "pmrl_indicators": (C.c_int, [c_void_p, i32, i32, i32, c_void_p, i32, c_void_p, c_void_p]),
     "pmrl_rollout_add": (C.c_int, [i32, i32, i32, i32, i32, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pmrl_rollout_gather": (C.c_int, [i32, i32, i32, i32, i32, i32, c_void_p, c_void_p,

@@ -148,3 +148,44 @@ class FixedFracDiff:
     @property
     def get_d_opt(self) -> dict:
         return self.d_opt
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Indicator windows (data/instrument.py:207-232; config/base.py:30-44)
+# ---------------------------------------------------------------------------------------------------------------
+INDICATOR_KINDS = {"sma": 0, "ema": 1, "rsi": 2, "atr": 3, "bbands": 4, "macd": 5}
+_IND_OUTPUTS = {"sma": ["sma"], "ema": ["ema"], "rsi": ["rsi"], "atr": ["atr"],
+                "bbands": ["upperband", "middleband", "lowerband"], "macd": ["macd", "macdsignal", "macdhist"]}
+_IND_DEFAULT_PERIOD = {"sma": 30, "ema": 30, "rsi": 14, "atr": 14, "bbands": 5, "macd": 0}
+
+
+def add_indicators(ohlcv, indicators):
+    """Instrument.add_indicators batched over assets (instrument.py:207-232).
+
+    ohlcv: [T, A, C>=4] (o, h, l, c[, v]); indicators: list of (name, params-dict) or a dict {name: params} like
+    config.base.INDICATORS (a list allows the same indicator with several periods).
+    Returns (names, out [A, n_out, T - lookback] float32, lookback): the outputs are clipped by the maximum lookback
+    exactly like the reference clips the instrument (`self.clip(start=lookback)`, :231)."""
+    import ctypes as C
+    lib = _lib.load()
+    items = list(indicators.items()) if isinstance(indicators, dict) else list(indicators)
+    tbl = _cuda_f32(ohlcv)
+    T, A, Cn = tbl.shape
+    specs, names = [], []
+    for name, params in items:
+        if name not in INDICATOR_KINDS:
+            raise NotImplementedError(f"indicator {name!r} is not implemented on device (have: {sorted(INDICATOR_KINDS)})")
+        period = int((params or {}).get("timeperiod", _IND_DEFAULT_PERIOD[name]))
+        specs += [INDICATOR_KINDS[name], period]
+        suffix = "_".join(str(v) for v in (params or {}).values())
+        names += [f"{o if o != name else name}_{suffix}" for o in _IND_OUTPUTS[name]]       # naming of :228-229
+    n = len(items)
+    arr = (C.c_int32 * (2 * n))(*specs)
+    n_out, lb = C.c_int32(0), C.c_int32(0)
+    _lib.check(lib.pmrl_indicator_layout(C.cast(arr, C.c_void_p), n, C.cast(C.byref(n_out), C.c_void_p),
+                                         C.cast(C.byref(lb), C.c_void_p)), "pmrl_indicator_layout")
+    series = tbl.permute(1, 2, 0).contiguous().view(A * Cn, T)
+    out = torch.empty(A, max(n_out.value, 1), T, dtype=torch.float32, device=tbl.device)
+    _lib.check(lib.pmrl_indicators(_lib.ptr(series), A, Cn, T, C.cast(arr, C.c_void_p), n, _lib.ptr(out), _lib.current_stream()),
+               "pmrl_indicators")
+    return names, out[:, :n_out.value, lb.value:].contiguous(), lb.value

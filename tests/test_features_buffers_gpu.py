@@ -268,3 +268,28 @@ def test_collect_loops_drive_env_and_buffers():
     total, met = loops.evaluate(env, act_fn, items)
     assert total.shape == (E,) and met.shape == (E, 4) and torch.isfinite(met).all() and torch.isfinite(total).all()
     assert np.isfinite(ora.value).all()
+
+
+# ---------------------------------------------------------------- indicator windows (N3)
+def test_indicator_windows_vs_oracle():
+    from oracle import indicators_oracle as io
+    from pmrl_b200 import features, synth
+    T, A = 600, 7
+    tbl = synth.gbm_ohlc(T, A, seed=9)
+    inds = [("ema", {"timeperiod": 30}), ("ema", {"timeperiod": 60}), ("bbands", {"timeperiod": 20}), ("macd", {}),
+            ("atr", {"timeperiod": 14}), ("rsi", {"timeperiod": 30}), ("sma", {"timeperiod": 10})]
+    names, out, lb = features.add_indicators(tbl, inds)
+    assert lb == 59 and out.shape == (A, 11, T - lb)
+    assert names[:2] == ["ema_30", "ema_60"] and names[2:5] == ["upperband_20", "middleband_20", "lowerband_20"]
+    got = out.cpu().numpy()
+    o, h, l, c = (tbl[:, :, i].numpy().T for i in range(4))
+    for a in range(A):
+        want = [io.ema(c[a], 30), io.ema(c[a], 60), *io.bbands(c[a], 20), *io.macd(c[a]), io.atr(h[a], l[a], c[a], 14),
+                io.rsi(c[a], 30), io.sma(c[a], 10)]
+        for j, w in enumerate(want):
+            np.testing.assert_allclose(got[a, j], w[lb:], rtol=2e-6, atol=1e-6, err_msg=f"asset {a} output {names[j]}")
+    assert np.isfinite(got).all()                              # nothing of the lookback survives the clip
+    # analytic checks: cash (asset 0, constant price): EMA = price, bands collapse, RSI = 0 (no gains), ATR = 0
+    np.testing.assert_allclose(got[0, 0], 1.0); np.testing.assert_allclose(got[0, 2], got[0, 4]); assert (got[0, 9] == 0).all()
+    with pytest.raises(NotImplementedError):
+        features.add_indicators(tbl, {"adx": {"timeperiod": 30}})
