@@ -32,7 +32,7 @@ def _cuda_f32(x, device=None):
 def ffd_weights(d, T: int, thres: float, device=None):
     """Binomial weights + widths per series (ffd.py:38-47).  d: [N] host floats (kept in fp64 like Python floats)."""
     lib = _lib.load()
-    d64 = torch.as_tensor(np.asarray(d, np.float64)).to(device or "cuda")
+    d64 = torch.tensor(np.asarray(d, np.float64), dtype=torch.float64).to(device or "cuda")
     N = d64.numel()
     w = torch.empty(N, T, dtype=torch.float32, device=d64.device)
     widths = torch.empty(N, dtype=torch.int32, device=d64.device)
