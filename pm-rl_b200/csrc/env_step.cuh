@@ -250,7 +250,7 @@ __device__ __forceinline__ void env_compute_store(const StepParams& p, int e, in
         if (p.ep_return) { epr = __fadd_rn(p.ep_return[e], r); p.ep_return[e] = epr; }
         if (p.stats) {
             acc[PMRL_STAT_N_ENVS] += 1.0; acc[PMRL_STAT_SUM_R] += r; acc[PMRL_STAT_SUM_R2] += (double)r * r;
-            acc[PMRL_STAT_SUM_V] += Vn; acc[PMRL_STAT_SUM_LNV] += log((double)Vn);
+            acc[PMRL_STAT_SUM_V] += Vn; acc[PMRL_STAT_SUM_LNV] += (double)logf(Vn);   // fp32 log: a double-precision log costs ~100 instructions per env
             if (dn) { acc[PMRL_STAT_N_DONE] += 1.0; acc[PMRL_STAT_SUM_EPRET] += epr; acc[PMRL_STAT_SUM_EPLEN] += k_new; }
             acc[PMRL_STAT_MAX_V] = fmax(acc[PMRL_STAT_MAX_V], (double)Vn);
             acc[PMRL_STAT_MAX_NEGV] = fmax(acc[PMRL_STAT_MAX_NEGV], -(double)Vn);
