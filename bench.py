@@ -78,7 +78,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -221,12 +221,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                                       # samples clocks / throttle reasons over warm-up + timed region
+        time.sleep(0.25)                                      # nvidia-smi needs a moment before its first sample
     for i in range(args.warmup):
         one_step(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
