@@ -113,8 +113,23 @@ def cpu_baseline(A, W, seconds=12.0):
     rate1 = time_port(A, W, 500, warmup=50)                      # calibrate (≈0.1 s)
     steps = max(500, int(rate1 * seconds))
     total, rates = time_port_all_cores(A, W, steps, procs)
+    # context only: the batched numpy restatement (oracle/env_oracle.py, one thread, state-only, no obs) — what a
+    # vectorised CPU rewrite of the reference would reach per core
+    import numpy as np
+    from oracle.env_oracle import OracleEnv
+    Eb = 4096
+    env = OracleEnv(Eb, A, W, 5)
+    rs = np.random.RandomState(0)
+    acts = rs.standard_normal((4, Eb, A)).astype(np.float32)
+    ys = (1 + 0.01 * rs.standard_normal((4, Eb, A))).astype(np.float32)
+    env.step(acts[0], ys[0])
+    t0 = time.perf_counter()
+    nb = 12
+    for i in range(nb):
+        env.step(acts[i % 4], ys[i % 4])
+    batched = nb * Eb * A / (time.perf_counter() - t0)
     return {"value": total * A, "unit": "asset-steps/s", "cores": procs, "kind": "port",
-            "env_steps_per_s": total,
+            "env_steps_per_s": total, "batched_numpy_1core_asset_steps_per_s": batched,
             "sample": f"{procs} single-thread processes x {steps} steps of one env ({A} assets, window {W}), "
                       f"oracle/ref_port.py (op-for-op torch-CPU port of env/sim/trading_env.py:44-105)"}
 
@@ -156,6 +171,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="env slices of the host-buffer step (H2D/kernel overlap)")
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (launch-bound small batches)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VAL",
                     help="kernel launch-shape override: rows|group|ctas|fused|fast = int (pmrl_set_tuning)")
@@ -253,7 +269,7 @@ def main():
         def e2e_step(i):
             # public host-buffer API: pinned actions in, reward/done out, the caller blocks until they are on the host.
             # Internally the batch is issued as 4 env slices so the H2D copy of slice c+1 overlaps the kernel of slice c.
-            env.step_host(h_act[i % 2], h_rew, h_done, obs=obs)
+            env.step_host(h_act[i % 2], h_rew, h_done, obs=obs, chunks=args.e2e_chunks)
 
         for i in range(3):
             e2e_step(i)
@@ -268,7 +284,7 @@ def main():
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
         e2e = {"value": world * E * A * args.steps / (float(ems.item()) * 1e-3), "unit": "asset-steps/s",
-               "h2d_bytes_per_step": E * A * 4, "d2h_bytes_per_step": E * 5,
+               "h2d_bytes_per_step": E * A * 4, "d2h_bytes_per_step": E * 5, "chunks": args.e2e_chunks,
                "ms_per_step": float(ems.item()) / args.steps}
 
     if rank == 0:
