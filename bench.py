@@ -128,8 +128,14 @@ def cpu_baseline(A, W, seconds=12.0):
     for i in range(nb):
         env.step(acts[i % 4], ys[i % 4])
     batched = nb * Eb * A / (time.perf_counter() - t0)
+    try:                                                      # plain-C restatement with OpenMP over all cores (state-only)
+        from oracle.c_oracle import time_all_cores
+        c_port = time_all_cores(A, W)
+    except Exception:
+        c_port = None
     return {"value": total * A, "unit": "asset-steps/s", "cores": procs, "kind": "port",
             "env_steps_per_s": total, "batched_numpy_1core_asset_steps_per_s": batched,
+            "c_port_openmp_all_cores_asset_steps_per_s": c_port,
             "sample": f"{procs} single-thread processes x {steps} steps of one env ({A} assets, window {W}), "
                       f"oracle/ref_port.py (op-for-op torch-CPU port of env/sim/trading_env.py:44-105)"}
 

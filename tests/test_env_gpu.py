@@ -378,3 +378,37 @@ def test_step_host_chunked_matches_step(chunks):
     compare_state(gpu, ora, "end")
     compare_obs(obs, ora, "end")
     assert gpu.stats()["n_envs"] == E * (L + 4) - E      # one auto-reset call per env is not a step
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_shape_fuzz(seed):
+    """Random (E, A, W, F, commission, reward, episode length) against the oracle: every dispatch path gets exercised
+    (RT / register-ring / generic fused kernels, state-only pipelined and plain kernels, partial groups and tiles)."""
+    rs = np.random.RandomState(1000 + seed)
+    A = int(rs.choice([1, 2, 5, 16, 31, 32, 36, 50, 64, 100, 128, 129, 200, 300]))
+    W = int(rs.choice([2, 3, 8, 17, 32, 50, 64, 65]))
+    F = int(rs.choice([5, 5, 5, 2, 4, 7]))
+    E = int(rs.randint(1, 70))
+    L = int(rs.randint(2, W + 6))
+    c = float(rs.choice([0.0, 0.0, 0.0025, 0.02]))
+    reward = str(rs.choice(["step_log", "returns", "log_returns"]))
+    gpu, ora = make_pair(E, A, W, F, episode_len=L, commission=c, reward=reward, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    obs = gpu.reset()
+    compare_obs(obs, ora, "reset")
+    for s in range(2 * L + 3):
+        kind = s % 4
+        act = torch.randn(E, A, generator=g)
+        if kind == 1:
+            act = torch.softmax(act, dim=1)
+        elif kind == 2:
+            act = torch.rand(E, A, generator=g) + 1e-3                 # non-negative, not a simplex (quirk Q1): sum in [0.8, 1.2]
+            act = act / act.sum(1, keepdim=True) * (0.8 + 0.4 * torch.rand(E, 1, generator=g))
+        want_obs = bool(rs.randint(0, 2))
+        obs, r, done = gpu.step(act.cuda(), obs=want_obs)
+        r_o, d_o = ora.step(act.numpy())
+        np.testing.assert_array_equal(done.cpu().numpy(), d_o, err_msg=f"done @ {s}")
+        util.assert_rewards_close(r.cpu().numpy(), r_o, f"step {s}")
+        if want_obs:
+            compare_obs(obs, ora, f"obs @ {s}")
+    compare_state(gpu, ora, "end")
