@@ -13,43 +13,61 @@
 
 namespace pmrl {
 
-// One thread per series: torch.cumprod on the CPU multiplies left to right with a *double* accumulator
-// (ATen acc_type<float>) and rounds every prefix to fp32, so the chain is reproduced bit for bit the same
-// way; N is a few hundred at most.
-__global__ void k_ffd_weights(const double* __restrict__ d, int N, int T, float thres,
-                              float* __restrict__ weights, int32_t* __restrict__ widths) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+// One block per series.  torch.cumprod on the CPU multiplies left to right with a *double* accumulator (ATen
+// acc_type<float>) and rounds every prefix to fp32, so the chain is reproduced bit for bit the same way: the
+// factors 1 - (d+1)/k are independent (all threads, fp32 like torch.div(...)+1), only the running product is a
+// sequential scan (one thread, one DMUL per element, factors staged through shared memory).
+constexpr int kWThreads = 128;
+constexpr int kWChunk = 2048;
+
+__global__ void __launch_bounds__(kWThreads) k_ffd_weights(const double* __restrict__ d, int T, float thres,
+                                                           float* __restrict__ weights, int32_t* __restrict__ widths) {
+    __shared__ float s_proto[kWChunk];
+    const int n = blockIdx.x, tid = threadIdx.x;
     const float factor = (float)(-(d[n] + 1.0));           // zeros(len-1) - (d+1)        (ffd.py:38)
     float* __restrict__ w = weights + (size_t)n * T;
     double acc = 1.0;
     int width = 0;
-    w[0] = 1.0f;
-    for (int k = 1; k < T; ++k) {
-        const float proto = __fadd_rn(__fdiv_rn(factor, (float)k), 1.0f);   // div(factor, k) + 1  (ffd.py:39)
-        acc *= (double)proto;                                                // cumprod             (ffd.py:40)
-        const float wk = (float)acc;
-        w[k] = wk;
-        if (fabsf(wk) > thres) width = k;                                    // where(|w|>thres).max() (ffd.py:43)
+    for (int k0 = 0; k0 < T; k0 += kWChunk) {
+        const int kc = min(kWChunk, T - k0);
+        __syncthreads();
+        for (int q = tid; q < kc; q += kWThreads) {
+            const int k = k0 + q;
+            s_proto[q] = k == 0 ? 1.0f : __fadd_rn(__fdiv_rn(factor, (float)k), 1.0f);    // div(factor, k) + 1  (ffd.py:39)
+        }
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll 8
+            for (int q = 0; q < kc; ++q) {
+                acc *= (double)s_proto[q];                   // cumprod                      (ffd.py:40)
+                const float wk = (float)acc;
+                s_proto[q] = wk;
+                if (fabsf(wk) > thres) width = k0 + q;       // where(|w|>thres).max()       (ffd.py:43)
+            }
+        }
+        __syncthreads();
+        for (int q = tid; q < kc; q += kWThreads) w[k0 + q] = s_proto[q];
     }
-    widths[n] = width;
+    if (tid == 0) widths[n] = width;
 }
 
 // Valid convolution with taps w[0:width] (tap `width` itself is dropped, ffd.py:47), tail-aligned:
 //   out[n, j] = Σ_{k<width} w[n,k] · x[n, max_width + j − k]
-// Block = (series n, tile of kTile outputs); taps are consumed in chunks of kChunk staged in shared memory
-// together with the matching x segment; each thread keeps kPer outputs in registers (fp32 FMA).
-constexpr int kConvThreads = 256;
-constexpr int kPer = 4;
+// Block = (series n, tile of 1024 outputs), 128 threads × 8 CONSECUTIVE outputs.  Taps are consumed in chunks of 256
+// staged in shared memory with the matching x segment.  Per group of 8 taps a thread keeps a 16-float register window
+// of x (two 16-byte shared loads refill it, the rest is reused from the previous group) and reads the 8 taps with two
+// broadcast 16-byte loads: 64 FMAs per 4 shared loads (the first version did 4 FMAs per 5 loads and was LDS-bound).
+constexpr int kConvThreads = 128;
+constexpr int kPer = 8;
 constexpr int kTile = kConvThreads * kPer;     // 1024 outputs per block
-constexpr int kChunk = 512;                    // taps per stage
+constexpr int kChunk = 256;                    // taps per stage (multiple of 8)
 
 __global__ void __launch_bounds__(kConvThreads) k_ffd_conv(const float* __restrict__ x, const double* __restrict__ d,
                                                            const float* __restrict__ weights,
                                                            const int32_t* __restrict__ widths,
                                                            int T, int max_width, float* __restrict__ out) {
-    __shared__ float s_w[kChunk];
-    __shared__ float s_x[kTile + kChunk];
+    __shared__ __align__(16) float s_w[kChunk];
+    __shared__ __align__(16) float s_x[kTile + kChunk];
     const int n = blockIdx.y;
     const int j0 = blockIdx.x * kTile;
     const int Tout = T - max_width;
@@ -69,29 +87,39 @@ __global__ void __launch_bounds__(kConvThreads) k_ffd_conv(const float* __restri
 #pragma unroll
     for (int r = 0; r < kPer; ++r) acc[r] = 0.0f;
     for (int k0 = 0; k0 < width; k0 += kChunk) {
-        const int kc = min(kChunk, width - k0);
-        // x segment needed: indices max_width + j − k for j ∈ [j0, j0+kTile), k ∈ [k0, k0+kc)
-        const int lo = max_width + j0 - (k0 + kc - 1);       // may be < 0 only for out-of-range taps (masked below)
-        const int seg = kTile + kc - 1;
+        // s_w[kk] = w[k0+kk] (0 beyond `width`); s_x[i] = x[lo + i] with lo = max_width + j0 − (k0 + kChunk − 1), so that the
+        // operand of output j0 + 8t + r and tap k0 + kk sits at s_x[8t + r + (kChunk − 1) − kk]
+        const int lo = max_width + j0 - (k0 + kChunk - 1);
         __syncthreads();
-        for (int q = tid; q < kc; q += kConvThreads) s_w[q] = wn[k0 + q];
-        for (int q = tid; q < seg; q += kConvThreads) {
+        for (int q = tid; q < kChunk; q += kConvThreads) s_w[q] = (k0 + q < width) ? wn[k0 + q] : 0.0f;
+        for (int q = tid; q < kTile + kChunk; q += kConvThreads) {
             const int xi = lo + q;
             s_x[q] = (xi >= 0 && xi < T) ? xn[xi] : 0.0f;
         }
         __syncthreads();
-        // output j = j0 + tid + r*kConvThreads ; x index offset in segment = (j − j0) + (kc−1) − kk
-#pragma unroll 4
-        for (int kk = 0; kk < kc; ++kk) {
-            const float wk = s_w[kk];
-            const int base = tid + (kc - 1) - kk;
+        const int ngroups = (min(kChunk, width - k0) + 7) >> 3;
+        int wb = 8 * tid + kChunk - 8;                       // window base of group 0 (a multiple of 4 floats)
+        float xw[16];
+        {
+            const float4 a0 = *reinterpret_cast<const float4*>(s_x + wb + 8), a1 = *reinterpret_cast<const float4*>(s_x + wb + 12);
+            xw[0] = a0.x; xw[1] = a0.y; xw[2] = a0.z; xw[3] = a0.w; xw[4] = a1.x; xw[5] = a1.y; xw[6] = a1.z; xw[7] = a1.w;
+        }
+        for (int g = 0; g < ngroups; ++g, wb -= 8) {
 #pragma unroll
-            for (int r = 0; r < kPer; ++r) acc[r] = fmaf(wk, s_x[base + r * kConvThreads], acc[r]);
+            for (int i = 0; i < 8; ++i) xw[8 + i] = xw[i];   // the upper half of the window is the previous lower half
+            const float4 b0 = *reinterpret_cast<const float4*>(s_x + wb), b1 = *reinterpret_cast<const float4*>(s_x + wb + 4);
+            xw[0] = b0.x; xw[1] = b0.y; xw[2] = b0.z; xw[3] = b0.w; xw[4] = b1.x; xw[5] = b1.y; xw[6] = b1.z; xw[7] = b1.w;
+            const float4 t0 = *reinterpret_cast<const float4*>(s_w + 8 * g), t1 = *reinterpret_cast<const float4*>(s_w + 8 * g + 4);
+            const float tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int r = 0; r < kPer; ++r) acc[r] = fmaf(tw[u], xw[7 - u + r], acc[r]);
         }
     }
 #pragma unroll
     for (int r = 0; r < kPer; ++r) {
-        const int j = j0 + tid + r * kConvThreads;
+        const int j = j0 + 8 * tid + r;
         if (j < Tout) on[j] = acc[r];
     }
 }
@@ -186,7 +214,7 @@ extern "C" int pmrl_ffd_weights(const double* d, int32_t N, int32_t T, float thr
     if (N < 0 || T < 2) return pmrl_fail(PMRL_E_SHAPE, "ffd_weights: N >= 0 and T >= 2 required");
     if (T > (1 << 24)) return pmrl_fail(PMRL_E_SHAPE, "ffd_weights: T must stay exactly representable in fp32");
     if (N == 0) return 0;
-    k_ffd_weights<<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(d, N, T, thres, weights, widths);
+    k_ffd_weights<<<N, kWThreads, 0, (cudaStream_t)stream>>>(d, T, thres, weights, widths);
     return pmrl_check_launch("k_ffd_weights");
 }
 

@@ -36,6 +36,15 @@ def main():
     flops = 2.0 * sum(int(w) for w in widths) * (T - mw)
     print(json.dumps({"bench": "ffd_transform", "series": A * 4, "rows": T, "d": 0.4, "thres": 1e-5, "width": int(widths[0]),
                       "max_width": mw, "ms": ms, "gflops": flops / ms / 1e6, "note": "weights + conv (+ one host read of the widths)"}))
+    from pmrl_b200 import _lib
+    lib = _lib.load()
+    wts, wd, d64 = features.ffd_weights(d, T, 1e-5)
+    outb = torch.empty(A * 4, T - mw, device="cuda")
+    ms_w = timeit(lambda: features.ffd_weights(d, T, 1e-5), n=5)
+    ms_cv = timeit(lambda: _lib.check(lib.pmrl_ffd_transform(series.data_ptr(), d64.data_ptr(), wts.data_ptr(), wd.data_ptr(), A * 4, T, mw,
+                                                             outb.data_ptr(), _lib.current_stream()), "ffd"), n=10)
+    print(json.dumps({"bench": "k_ffd_weights (400 series x 12,000 factors, sequential double cumprod)", "ms": ms_w}))
+    print(json.dumps({"bench": "k_ffd_conv alone", "ms": ms_cv, "gflops": flops / ms_cv / 1e6, "fp32_peak_note": "B200 fp32 FMA peak ~75 TFLOP/s"}))
     ms_tab = timeit(lambda: features.build_env_tables(tbl, d=0.4, thres=1e-5, scaler="minmax"), n=5)
     print(json.dumps({"bench": "build_env_tables(ffd + minmax + pack)", "ms": ms_tab}))
     # ---- config 3: off-policy collect on FFD features: step (obs) + index-replay write ----
