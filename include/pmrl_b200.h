@@ -183,13 +183,18 @@ int pmrl_pack_features(const float* series, const float* close, int32_t A, int32
  * fp32 with NaN over each indicator's lookback — TA-Lib is not vendored: parity UNPINNED).
  * specs: HOST array [n_specs, 2] of (PMRL_IND_*, period); series [A*C, L] with channels o,h,l,c[,v] (index a*C + c);
  * out [A, n_out, L] where n_out / the maximum lookback come from pmrl_indicator_layout (BBANDS: upper, middle, lower;
- * MACD 12/26/9: macd, signal, hist; the others one output). */
+ * MACD 12/26/9: macd, signal, hist; STOCH 5/3/3: slowk, slowd; the others one output).  ADX / DX of the reference's
+ * commented default list are not implemented (their TA-Lib seeding cannot be verified here). */
 #define PMRL_IND_SMA    0
 #define PMRL_IND_EMA    1
 #define PMRL_IND_RSI    2
 #define PMRL_IND_ATR    3
 #define PMRL_IND_BBANDS 4
 #define PMRL_IND_MACD   5
+#define PMRL_IND_OBV    6   /* needs the volume channel (C >= 5) */
+#define PMRL_IND_ADOSC  7   /* 3 / 10; needs the volume channel */
+#define PMRL_IND_CCI    8
+#define PMRL_IND_STOCH  9   /* 5 / 3 / 3: slowk, slowd */
 int pmrl_indicator_layout(const int32_t* specs, int32_t n_specs, int32_t* n_out, int32_t* lookback);
 int pmrl_indicators(const float* series, int32_t A, int32_t C, int32_t L, const int32_t* specs, int32_t n_specs,
                     float* out, void* stream);

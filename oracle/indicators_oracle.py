@@ -69,3 +69,50 @@ def macd(c):
         t = q + 25
         m[t], sg[t], hs[t] = raw[q], eg, raw[q] - eg
     return m.astype(np.float32), sg.astype(np.float32), hs.astype(np.float32)
+
+
+def obv(c, v):
+    c, v = np.asarray(c, np.float64), np.asarray(v, np.float64); out = np.empty(len(c)); out[0] = v[0]
+    for t in range(1, len(c)):
+        out[t] = out[t - 1] + (v[t] if c[t] > c[t - 1] else -v[t] if c[t] < c[t - 1] else 0.0)
+    return out.astype(np.float32)
+
+
+def adosc(h, l, c, v):
+    h, l, c, v = (np.asarray(x, np.float64) for x in (h, l, c, v)); out = np.full(len(c), np.nan)
+    ad = 0.0; kf, ks = 2 / 4.0, 2 / 11.0
+    for t in range(len(c)):
+        rng = h[t] - l[t]
+        if rng > 0:
+            ad += ((c[t] - l[t]) - (h[t] - c[t])) / rng * v[t]
+        if t == 0:
+            ef = es = ad
+        else:
+            ef = (ad - ef) * kf + ef; es = (ad - es) * ks + es
+        if t >= 9:
+            out[t] = ef - es
+    return out.astype(np.float32)
+
+
+def cci(h, l, c, n):
+    tp = (np.asarray(h, np.float64) + np.asarray(l, np.float64) + np.asarray(c, np.float64)) / 3.0
+    out = np.full(len(tp), np.nan)
+    for t in range(n - 1, len(tp)):
+        w = tp[t - n + 1:t + 1]; m = w.mean(); md = np.abs(w - m).mean()
+        out[t] = (tp[t] - m) / (0.015 * md) if md != 0 else 0.0
+    return out.astype(np.float32)
+
+
+def stoch(h, l, c):
+    h, l, c = (np.asarray(x, np.float64) for x in (h, l, c)); L = len(c)
+    fk = np.full(L, np.nan)
+    for t in range(4, L):
+        hh, ll = h[t - 4:t + 1].max(), l[t - 4:t + 1].min()
+        fk[t] = 100 * (c[t] - ll) / (hh - ll) if hh != ll else 0.0
+    sk = np.full(L, np.nan); sd = np.full(L, np.nan)
+    for t in range(6, L):
+        sk[t] = fk[t - 2:t + 1].mean()
+    for t in range(8, L):
+        sd[t] = sk[t - 2:t + 1].mean()
+    sk[:8] = np.nan
+    return sk.astype(np.float32), sd.astype(np.float32)

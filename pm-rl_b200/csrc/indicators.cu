@@ -26,6 +26,7 @@ __global__ void k_indicators(const float* __restrict__ series, int A, int C, int
     const float* __restrict__ hi = series + ((size_t)a * C + 1) * L;
     const float* __restrict__ lo = series + ((size_t)a * C + 2) * L;
     const float* __restrict__ cl = series + ((size_t)a * C + 3) * L;
+    const float* __restrict__ vo = series + ((size_t)a * C + (C > 4 ? 4 : 3)) * L;   // volume (needs C >= 5)
     float* __restrict__ o0 = out + ((size_t)a * n_out + sp.out0[s]) * L;
     float* __restrict__ o1 = o0 + L;
     float* __restrict__ o2 = o1 + L;
@@ -111,6 +112,56 @@ __global__ void k_indicators(const float* __restrict__ series, int A, int C, int
             }
         }
     } break;
+    case PMRL_IND_OBV: {                                                                      // on-balance volume
+        double obv = 0.0;
+        for (int t = 0; t < L; ++t) {
+            const double v = (double)vo[t];
+            if (t == 0) obv = v;
+            else if (cl[t] > cl[t - 1]) obv += v;
+            else if (cl[t] < cl[t - 1]) obv -= v;
+            o0[t] = (float)obv;
+        }
+    } break;
+    case PMRL_IND_ADOSC: {                                                                    // Chaikin A/D oscillator, EMA3 - EMA10 of the A/D line
+        const double kf = 2.0 / 4.0, ks = 2.0 / 11.0;
+        double ad = 0.0, ef = 0.0, es = 0.0;
+        for (int t = 0; t < L; ++t) {
+            const double h = hi[t], l = lo[t], c = cl[t], v = vo[t];
+            const double rng = h - l;
+            if (rng > 0.0) ad += (((c - l) - (h - c)) / rng) * v;
+            if (t == 0) { ef = ad; es = ad; }
+            else { ef = (ad - ef) * kf + ef; es = (ad - es) * ks + es; }
+            o0[t] = t >= 9 ? (float)(ef - es) : nan;
+        }
+    } break;
+    case PMRL_IND_CCI: {                                                                      // (TP - SMA(TP)) / (0.015 * mean deviation)
+        for (int t = 0; t < L; ++t) {
+            if (t < n - 1) { o0[t] = nan; continue; }
+            double sum = 0.0;
+            for (int i = t - n + 1; i <= t; ++i) sum += ((double)hi[i] + (double)lo[i] + (double)cl[i]) / 3.0;
+            const double m = sum / n;
+            double md = 0.0;
+            for (int i = t - n + 1; i <= t; ++i) md += fabs(((double)hi[i] + (double)lo[i] + (double)cl[i]) / 3.0 - m);
+            md /= n;
+            const double tp = ((double)hi[t] + (double)lo[t] + (double)cl[t]) / 3.0;
+            o0[t] = (float)(md != 0.0 ? (tp - m) / (0.015 * md) : 0.0);
+        }
+    } break;
+    case PMRL_IND_STOCH: {                                                                    // fastK 5, slowK = SMA3(fastK), slowD = SMA3(slowK)
+        double fk[3] = {0, 0, 0}, sk[3] = {0, 0, 0};
+        for (int t = 0; t < L; ++t) {
+            if (t < 4) { o0[t] = nan; o1[t] = nan; continue; }
+            double hh = hi[t], ll = lo[t];
+            for (int i = t - 4; i < t; ++i) { hh = fmax(hh, (double)hi[i]); ll = fmin(ll, (double)lo[i]); }
+            const double diff = hh - ll;
+            fk[t % 3] = diff != 0.0 ? 100.0 * ((double)cl[t] - ll) / diff : 0.0;
+            if (t < 6) { o0[t] = nan; o1[t] = nan; continue; }
+            const double slowk = (fk[0] + fk[1] + fk[2]) / 3.0;
+            sk[t % 3] = slowk;
+            if (t < 8) { o0[t] = nan; o1[t] = nan; continue; }
+            o0[t] = (float)slowk; o1[t] = (float)((sk[0] + sk[1] + sk[2]) / 3.0);
+        }
+    } break;
     default: break;
     }
 }
@@ -119,12 +170,16 @@ __global__ void k_indicators(const float* __restrict__ series, int A, int C, int
 
 using namespace pmrl;
 
-static int spec_outputs(int kind) { return (kind == PMRL_IND_BBANDS || kind == PMRL_IND_MACD) ? 3 : 1; }
+static int spec_outputs(int kind) { return (kind == PMRL_IND_BBANDS || kind == PMRL_IND_MACD) ? 3 : (kind == PMRL_IND_STOCH ? 2 : 1); }
 static int spec_lookback(int kind, int n) {
     switch (kind) {
         case PMRL_IND_SMA: case PMRL_IND_EMA: case PMRL_IND_BBANDS: return n - 1;
         case PMRL_IND_RSI: case PMRL_IND_ATR: return n;
         case PMRL_IND_MACD: return 25 + 8;
+        case PMRL_IND_OBV: return 0;
+        case PMRL_IND_ADOSC: return 9;
+        case PMRL_IND_CCI: return n - 1;
+        case PMRL_IND_STOCH: return 8;
         default: return -1;
     }
 }
@@ -135,7 +190,8 @@ extern "C" int pmrl_indicator_layout(const int32_t* specs, int32_t n_specs, int3
     for (int i = 0; i < n_specs; ++i) {
         const int kind = specs[2 * i], n = specs[2 * i + 1];
         const int l = spec_lookback(kind, n);
-        if (l < 0 || (kind != PMRL_IND_MACD && n < 2)) return pmrl_fail(PMRL_E_ARG, "indicator_layout: unknown indicator or period < 2");
+        const bool fixed = kind == PMRL_IND_MACD || kind == PMRL_IND_OBV || kind == PMRL_IND_ADOSC || kind == PMRL_IND_STOCH;
+        if (l < 0 || (!fixed && n < 2)) return pmrl_fail(PMRL_E_ARG, "indicator_layout: unknown indicator or period < 2");
         no += spec_outputs(kind);
         if (l > lb) lb = l;
     }
@@ -151,6 +207,8 @@ extern "C" int pmrl_indicators(const float* series, int32_t A, int32_t C, int32_
     int n_out = 0, lb = 0;
     if (int rc = pmrl_indicator_layout(specs, n_specs, &n_out, &lb)) return rc;
     if (n_specs == 0) return 0;
+    for (int i = 0; i < n_specs; ++i)
+        if ((specs[2 * i] == PMRL_IND_OBV || specs[2 * i] == PMRL_IND_ADOSC) && C < 5) return pmrl_fail(PMRL_E_SHAPE, "indicators: OBV / ADOSC need the volume channel (C >= 5)");
     IndSpecs sp;
     sp.n = n_specs;
     int o = 0;

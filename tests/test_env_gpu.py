@@ -163,6 +163,23 @@ def test_thousand_step_rollout_within_north_star_tolerance(A, seed):
     assert done.cpu().numpy().all()
 
 
+def test_thousand_step_rollout_through_the_fused_obs_kernel():
+    """The same 1,000-step bound with the observation materialised every step (default fused RT kernel path)."""
+    E, A, W, L = 24, 100, 50, 1000
+    gpu, ora = make_pair(E, A, W, 5, T=W + L + 40, episode_len=L, seed=5)
+    g = torch.Generator().manual_seed(55)
+    gpu.reset()
+    for s in range(L):
+        act = torch.randn(E, A, generator=g)
+        obs, r, done = gpu.step(act.cuda())
+        r_o, d_o = ora.step(act.numpy())
+        if s in (0, 48, 49, 50, 499, 999):
+            util.assert_rewards_close(r.cpu().numpy(), r_o, f"step {s}")
+            compare_state(gpu, ora, f"step {s}")
+            compare_obs(obs, ora, f"obs @ {s}")
+    assert done.cpu().numpy().all()
+
+
 @pytest.mark.parametrize("reward", ["returns", "log_returns", "sharpe_ratio"])
 @pytest.mark.parametrize("commission", [0.0, 0.0025])
 def test_reward_variants_and_commission(reward, commission):

@@ -293,3 +293,23 @@ def test_indicator_windows_vs_oracle():
     np.testing.assert_allclose(got[0, 0], 1.0); np.testing.assert_allclose(got[0, 2], got[0, 4]); assert (got[0, 9] == 0).all()
     with pytest.raises(NotImplementedError):
         features.add_indicators(tbl, {"adx": {"timeperiod": 30}})
+
+
+def test_volume_and_oscillator_indicators_vs_oracle():
+    from oracle import indicators_oracle as io
+    from pmrl_b200 import features, synth
+    T, A = 400, 5
+    tbl4 = synth.gbm_ohlc(T, A, seed=11)
+    vol = (1e5 * (1 + torch.rand(T, A, generator=torch.Generator().manual_seed(1)))).unsqueeze(-1)
+    tbl = torch.cat([tbl4, vol], dim=-1)                            # o, h, l, c, v
+    names, out, lb = features.add_indicators(tbl, [("obv", {}), ("adosc", {}), ("cci", {"timeperiod": 14}), ("stoch", {})])
+    assert lb == 13 and out.shape == (A, 5, T - lb) and names[3:] == ["slowk_", "slowd_"]
+    got = out.cpu().numpy()
+    o, h, l, c, v = (tbl[:, :, i].numpy().T for i in range(5))
+    for a in range(1, A):
+        want = [io.obv(c[a], v[a]), io.adosc(h[a], l[a], c[a], v[a]), io.cci(h[a], l[a], c[a], 14), *io.stoch(h[a], l[a], c[a])]
+        for j, w in enumerate(want):
+            np.testing.assert_allclose(got[a, j], w[lb:], rtol=3e-5, atol=1e-3 * max(1.0, float(np.nanmax(np.abs(w[lb:])))) * 1e-3,
+                                       err_msg=f"asset {a} {names[j]}")
+    with pytest.raises(Exception):
+        features.add_indicators(tbl4, [("obv", {})])               # needs the volume channel
