@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+#include <mutex>
 #include "pmrl_b200.h"
 #include "pmrl_device.cuh"
 #include "env_step.cuh"
@@ -221,11 +222,13 @@ struct TmapKey { const void* ptr; int A, T, W, TR, dev; };
 static TmapKey g_keys[8];
 static CUtensorMap g_maps[8];
 static int g_nmaps = 0, g_next = 0;
+static std::mutex g_tmap_mutex;
 
 static int get_tmap(const StepParams& p, int TR, CUtensorMap* out) {
     int dev = 0;
     cudaGetDevice(&dev);
     TmapKey key{p.feat_am, p.A, p.T, p.W, TR, dev};
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
     for (int i = 0; i < g_nmaps; ++i)
         if (memcmp(&g_keys[i], &key, sizeof(key)) == 0) { *out = g_maps[i]; return 0; }
     static EncodeTiledFn encode = nullptr;
