@@ -148,6 +148,7 @@ def run_reference(args, rank, world):
     t0 = time.perf_counter()
     # each "step" of this arm is a bounded sample: all cores stepping single envs for a fixed wall time
     per = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    per = float(os.environ.get("PMRL_BENCH_REF_SECONDS", per))          # tests shrink the sample
     vals = []
     for i in range(args.warmup + args.steps):
         b = cpu_baseline(A, W, seconds=per)
