@@ -229,6 +229,11 @@ def main():
     for i in range(preroll):
         env.step(pool[i % n_pool], obs=False)
 
+    # multi-GPU: the 10-double stats vector is all-reduced over NCCL EVERY step (SURVEY.md §8(e), K = 1), issued
+    # asynchronously behind a snapshot so the next step's kernel is not ordered after the collective
+    reducer = pdist.AsyncStatsReducer(dev) if world > 1 else None
+    stats_in_sync = None
+
     if args.graph:
         static_actions, replay = env.graphed_step(obs=obs)
 
@@ -238,6 +243,8 @@ def main():
     else:
         def one_step(i):
             env.step(pool[i % n_pool], obs=obs)
+            if reducer is not None:
+                reducer.launch(env._stats)
 
     def barrier():
         if world > 1:
@@ -264,6 +271,10 @@ def main():
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
+    if reducer is not None:                                   # the last step's reduced vector must equal a fresh reduce
+        last = reducer.result()
+        fresh = pdist.all_reduce_stats(env._stats.clone())
+        stats_in_sync = bool(torch.allclose(last, fresh, rtol=1e-12, atol=0.0))
     stats = env.stats(all_reduce=world > 1)                   # NCCL all-reduce of the 10-double stats vector
 
     # ---- end to end through the public API with host buffers (H2D actions, D2H reward/done every step) ----
@@ -309,7 +320,7 @@ def main():
             "config": {"workload": args.workload, "description": desc, "envs_per_gpu": E, "envs_total": world * E,
                        "assets": A, "window": W, "features": F, "commission": commission, "obs_materialised": obs,
                        "episode_len": EPISODE_LEN, "table_rows": TABLE_ROWS, "preroll_steps": preroll, "tune": args.tune, "cuda_graph": bool(args.graph), "actions": "raw N(0,1) scores (softmax branch)",
-                       "parallelism": f"env-shard x{world}, NCCL stats all-reduce",
+                       "parallelism": f"env-shard x{world}, no data-path collective" + (", NCCL stats all-reduce every step (async)" if world > 1 else ""),
                        "l2_policy": "working set per step (obs write + ring) exceeds L2 (126 MB)" if E * A * W * 4 > 126e6
                                     else "working set smaller than L2: L2-resident by construction"},
             "roofline": {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak,
@@ -320,6 +331,8 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "stats": {k: stats[k] for k in ("n_envs", "mean_reward", "mean_value", "n_done")},
         }
+        if reducer is not None:
+            line["stats_allreduce"] = {"every_steps": 1, "launches": reducer.launches, "last_equals_fresh_reduce": stats_in_sync}
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

@@ -45,3 +45,35 @@ def all_reduce_stats(stats: torch.Tensor) -> torch.Tensor:
     dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
     return torch.cat([sums, maxs])
+
+
+class AsyncStatsReducer:
+    """All-reduce of the statistics vector every step, off the step's critical path (one SUM over 8
+    doubles + one MAX over 2, K = 1 for config 4).  launch() snapshots the running vector into private buffers and
+    starts both collectives asynchronously (NCCL runs them on its own stream behind the snapshot); the next step's
+    kernel is not ordered after them.  result() waits and returns the reduced 10-vector of the last launch."""
+
+    def __init__(self, device, dtype=torch.float64):
+        self.sums = torch.zeros(N_SUM_STATS, dtype=dtype, device=device)
+        self.maxs = torch.zeros(2, dtype=dtype, device=device)
+        self.pending = []
+        self.launches = 0
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _drain(self):
+        for w in self.pending:
+            w.wait()                       # stream-level wait on a collective issued a whole step ago
+        self.pending = []
+
+    def launch(self, stats: torch.Tensor):
+        self._drain()
+        self.sums.copy_(stats[:N_SUM_STATS])
+        self.maxs.copy_(stats[N_SUM_STATS:])
+        if self.active:
+            self.pending = [dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, async_op=True),
+                            dist.all_reduce(self.maxs, op=dist.ReduceOp.MAX, async_op=True)]
+        self.launches += 1
+
+    def result(self) -> torch.Tensor:
+        self._drain()
+        return torch.cat([self.sums, self.maxs])

@@ -28,6 +28,14 @@ def test_all_reduce_stats_is_identity_without_a_group():
     assert torch.equal(pdist.all_reduce_stats(v), v)
 
 
+def test_async_reducer_is_a_snapshot_without_a_group():
+    ar = pdist.AsyncStatsReducer("cpu")
+    v = torch.arange(10, dtype=torch.float64)
+    ar.launch(v)
+    v += 1.0                                  # the running vector moves on; the snapshot does not
+    assert not ar.active and torch.equal(ar.result(), torch.arange(10, dtype=torch.float64))
+
+
 def _shard_stats(first, n, A, W, L, steps, seed):
     """Stats vector of envs [first, first+n) produced by the oracle; actions are keyed by the global env id."""
     from oracle.env_oracle import OracleEnv
@@ -57,6 +65,14 @@ def _worker(rank, world, port, E, out):
     lo, hi = pdist.shard_range(E, rank, world)
     st, vals = _shard_stats(lo, hi - lo, 7, 6, 9, 12, seed=3)
     red = pdist.all_reduce_stats(torch.from_numpy(st))
+    # the per-step asynchronous reducer: launch on a running vector several times, the last launch wins
+    ar = pdist.AsyncStatsReducer("cpu")
+    assert ar.active
+    running = torch.from_numpy(st) * 0.0
+    for frac in (0.25, 0.5, 1.0):
+        running = torch.from_numpy(st) * frac if frac < 1.0 else torch.from_numpy(st)
+        ar.launch(running)
+    assert ar.launches == 3 and torch.equal(ar.result(), red)
     out[rank] = (red.numpy().copy(), vals)
     dist.barrier()
     dist.destroy_process_group()
