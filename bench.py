@@ -178,7 +178,8 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="env slices of the host-buffer step (H2D/kernel overlap)")
+    ap.add_argument("--e2e-chunks", type=int, default=0,
+                    help="env slices of the host-buffer step: >0 geometric x2.5, <0 equal, 0 library default (5 geometric)")
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (launch-bound small batches)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VAL",
                     help="kernel launch-shape override: rows|group|ctas|fused|fast = int (pmrl_set_tuning)")
@@ -285,8 +286,8 @@ def main():
         h_done = torch.empty(E, dtype=torch.uint8).pin_memory()
 
         def e2e_step(i):
-            # public host-buffer API: pinned actions in, reward/done out, the caller blocks until they are on the host.
-            # Internally the batch is issued as 4 env slices so the H2D copy of slice c+1 overlaps the kernel of slice c.
+            # public host-buffer API (C-ABI pmrl_env_step_host): pinned actions in, reward/done out, the caller blocks until
+            # they are on the host.  Internally the batch is issued as env slices so the copies overlap the kernels.
             env.step_host(h_act[i % 2], h_rew, h_done, obs=obs, chunks=args.e2e_chunks)
 
         for i in range(3):
@@ -303,6 +304,9 @@ def main():
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
         e2e = {"value": world * E * A * args.steps / (float(ems.item()) * 1e-3), "unit": "asset-steps/s",
                "h2d_bytes_per_step": E * A * 4, "d2h_bytes_per_step": E * 5, "chunks": args.e2e_chunks,
+               "transfer": ("zero-copy: the step kernel reads the pinned host actions over PCIe; reward/done copied D2H"
+                            if args.e2e_chunks == 0 else "sliced H2D/D2H copies overlapped with per-slice kernels"),
+               "api": "BatchedTradingEnv.step_host -> C-ABI pmrl_env_step_host",
                "ms_per_step": float(ems.item()) / args.steps}
 
     if rank == 0:

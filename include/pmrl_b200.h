@@ -12,6 +12,7 @@
  *   pmrl_env_reset      <- TradingEnv.reset              env/sim/trading_env.py:21-41
  *                          ActionBuffer.reset            env/sim/weight_buffer.py:46-50
  *   pmrl_env_step       <- TradingEnv.step               env/sim/trading_env.py:44-105
+ *   pmrl_env_step_host  <- the same call with CPU tensors train/on_policy.py:64-65
  *                          ActionBuffer.update/get_last  env/sim/weight_buffer.py:13-30
  *                          ActionBuffer.get_all          env/sim/weight_buffer.py:32-44
  *                          Reward.get_reward & variants  env/reward.py:15-31
@@ -150,6 +151,20 @@ int pmrl_env_step(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvSta
                   const float* actions, const float* y_ext,
                   float* reward, uint8_t* done, float* obs, int32_t obs_mode,
                   double* stats, void* stream);
+
+/* The same transition driven from HOST buffers — the call the reference's loop makes with CPU tensors
+ * (`r, obs = env.step(action, …)` then `env.value` read on the host, train/on_policy.py:64-65).
+ *   actions_host [E, A]  host (pinned for overlap) in;  actions_stage [E, A] device staging buffer (caller-owned)
+ *   reward/done          device buffers as in pmrl_env_step;  reward_host [E] f32 / done_host [E] u8  host out
+ *   slices  0 (default): page-locked mapped actions_host → one kernel reads them in place over PCIe (zero-copy);
+ *                pageable → as slices = 5.   > 0: that many env slices growing ×2.5 (the H2D copy of slice c+1 and
+ *                the D2H copy of slice c-1 run under the kernel of slice c);  < 0: |slices| equal slices
+ * Unlike every other entry point this one BLOCKS until reward_host/done_host are written (it is not
+ * graph-capturable) and keeps two copy streams per device, created on first use. */
+int pmrl_env_step_host(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
+                       const float* actions_host, float* actions_stage,
+                       float* reward, uint8_t* done, float* reward_host, uint8_t* done_host,
+                       float* obs, int32_t obs_mode, double* stats, int32_t slices, void* stream);
 
 /* Materialise obs for the current state without stepping (obs_mode FULL or WEIGHTS). */
 int pmrl_obs_build(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,

@@ -175,62 +175,34 @@ class BatchedTradingEnv:
         return buf, self.reward, self.done
 
     # ------------------------------------------------------------------------------------------
-    def _chunk_structs(self, chunks: int):
-        """C structs for `chunks` contiguous env slices (envs are independent, so a step can be issued slice by slice)."""
-        key = int(chunks)
-        cache = self.__dict__.setdefault("_chunk_cache", {})
-        if key in cache:
-            return cache[key]
-        E = self.E
-        bounds = [(E * c) // chunks for c in range(chunks + 1)]
-        out = []
-        for lo, hi in zip(bounds[:-1], bounds[1:]):
-            n = hi - lo
-            cfg = _lib.PmrlEnvCfg.from_buffer_copy(self._c_cfg)
-            cfg.E = n
-            st = _lib.PmrlEnvState(_lib.ptr(self.value[lo:hi]), _lib.ptr(self.hist[lo:hi]), _lib.ptr(self.idx[lo:hi]),
-                                   _lib.ptr(self.is_full[lo:hi]), _lib.ptr(self.t[lo:hi]), _lib.ptr(self.t0[lo:hi]),
-                                   _lib.ptr(self.sharpe[lo:hi]) if self.sharpe is not None else None,
-                                   _lib.ptr(self.ep_return[lo:hi]))
-            out.append((lo, hi, cfg, st))
-        cache[key] = out
-        return out
-
-    def step_host(self, actions_host, reward_host=None, done_host=None, obs: bool = True, out=None, chunks: int = 4):
-        """One step driven from HOST buffers: `actions_host` [E, A] pinned float32 in, `reward_host` [E] / `done_host` [E]
-        pinned out.  The batch is issued as `chunks` contiguous env slices so that the host→device copy of slice c+1
-        overlaps the kernel of slice c (envs are independent).  Blocks until the results are on the host.
+    def step_host(self, actions_host, reward_host=None, done_host=None, obs: bool = True, out=None, chunks: int = 0):
+        """One step driven from HOST buffers (the reference loop's call with CPU tensors, train/on_policy.py:64-65):
+        `actions_host` [E, A] float32 (pinned, so the copies overlap) in, `reward_host` [E] f32 / `done_host` [E] u8 out.
+        With `chunks` = 0 and pinned actions the kernel reads them in place over PCIe (zero-copy, one launch); otherwise
+        pmrl_env_step_host issues the batch as env slices so that the host→device copy of slice c+1 and the
+        device→host copy of slice c-1 run under the kernel of slice c (`chunks` > 0: that many geometrically growing
+        slices, < 0: equal slices; pageable actions with 0: five slices).  Blocks until the results are on the host.
         Returns (obs | None, reward_host, done_host)."""
         E, A = self.E, self.A
-        dev = self.device
+        if actions_host.dtype != torch.float32 or actions_host.is_cuda or actions_host.numel() != E * A or not actions_host.is_contiguous():
+            raise _lib.PmrlError("step_host: actions_host must be a contiguous CPU float32 tensor of E*A elements")
         if reward_host is None:
             reward_host = torch.empty(E, dtype=torch.float32).pin_memory()
         if done_host is None:
             done_host = torch.empty(E, dtype=torch.uint8).pin_memory()
-        st = self.__dict__.setdefault("_host_step_state", None)
-        if st is None:
-            st = {"act": torch.empty(E, A, dtype=torch.float32, device=dev), "copy": torch.cuda.Stream(device=dev),
-                  "ev": [torch.cuda.Event() for _ in range(64)]}
-            self._host_step_state = st
-        d_act, copy_s = st["act"], st["copy"]
+        if (reward_host.dtype != torch.float32 or done_host.dtype != torch.uint8 or reward_host.numel() != E or done_host.numel() != E
+                or reward_host.is_cuda or done_host.is_cuda or not reward_host.is_contiguous() or not done_host.is_contiguous()):
+            raise _lib.PmrlError("step_host: reward_host [E] float32 / done_host [E] uint8 CPU tensors expected")
+        stage = self.__dict__.get("_host_stage")
+        if stage is None:
+            stage = self._host_stage = torch.empty(E, A, dtype=torch.float32, device=self.device)
         want_obs = obs and self.feat_am is not None
         buf = self._obs_buffer(out) if want_obs else None
-        main = torch.cuda.current_stream(dev)
-        copy_s.wait_stream(main)                              # the previous step no longer reads d_act
-        a2 = actions_host.reshape(E, A)
-        for c, (lo, hi, cfg, cst) in enumerate(self._chunk_structs(chunks)):
-            with torch.cuda.stream(copy_s):
-                d_act[lo:hi].copy_(a2[lo:hi], non_blocking=True)
-                st["ev"][c].record(copy_s)
-            main.wait_event(st["ev"][c])
-            rc = self.lib.pmrl_env_step(C.byref(cfg), self._p_tbl, C.byref(cst), d_act[lo:hi].data_ptr(), None,
-                                        self.reward[lo:hi].data_ptr(), self.done[lo:hi].data_ptr(),
-                                        _lib.ptr(buf[lo:hi]) if buf is not None else None,
-                                        OBS_FULL if want_obs else OBS_NONE, _lib.ptr(self._stats), main.cuda_stream)
-            _lib.check(rc, "pmrl_env_step")
-            reward_host[lo:hi].copy_(self.reward[lo:hi], non_blocking=True)
-            done_host[lo:hi].copy_(self.done[lo:hi], non_blocking=True)
-        main.synchronize()
+        rc = self.lib.pmrl_env_step_host(self._p_cfg, self._p_tbl, self._p_st, actions_host.data_ptr(), stage.data_ptr(),
+                                         self.reward.data_ptr(), self.done.data_ptr(), reward_host.data_ptr(),
+                                         done_host.data_ptr(), _lib.ptr(buf), OBS_FULL if want_obs else OBS_NONE,
+                                         _lib.ptr(self._stats), int(chunks), _lib.current_stream())
+        _lib.check(rc, "pmrl_env_step_host")
         return buf, reward_host, done_host
 
     def graphed_step(self, obs: bool = True, out=None):

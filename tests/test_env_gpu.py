@@ -378,16 +378,19 @@ def test_window_of_one_is_rejected_like_the_reference_would_fail():
         Env(pmrl.EnvConfig(num_envs=2, num_assets=3, window_size=1, episode_len=0))
 
 
-@pytest.mark.parametrize("chunks", [1, 3, 4])
-def test_step_host_chunked_matches_step(chunks):
-    """Host-buffer step (H2D of slice c+1 overlapping the kernel of slice c) gives the same transition as step()."""
-    E, A, W, L = 50, 40, 8, 30
+@pytest.mark.parametrize("E,chunks,pinned", [(50, 1, True), (50, 4, True), (700, 0, True), (700, 0, False), (700, 3, True), (700, -4, False),
+                                             (1500, 6, True), (333, -32, True), (4096, 0, True)])
+def test_step_host_chunked_matches_step(E, chunks, pinned):
+    """Host-buffer step through pmrl_env_step_host (H2D of slice c+1 / D2H of slice c-1 under the kernel of slice c;
+    geometric, equal and degenerate slicings) gives the same transition as the oracle."""
+    A, W, L = 40, 8, 30
     gpu, ora = make_pair(E, A, W, 5, episode_len=L, collect_stats=True)
     gpu.reset()
     g = torch.Generator().manual_seed(11)
     h_r = torch.empty(E, dtype=torch.float32).pin_memory(); h_d = torch.empty(E, dtype=torch.uint8).pin_memory()
     for s in range(L + 4):
-        act = torch.randn(E, A, generator=g).pin_memory()
+        act = torch.randn(E, A, generator=g)
+        act = act.pin_memory() if pinned else act               # pinned + chunks 0 → the kernel reads host memory in place
         obs, r, d = gpu.step_host(act, h_r, h_d, chunks=chunks)
         r_o, d_o = ora.step(act.numpy())
         util.assert_rewards_close(r.numpy(), r_o, f"step {s}")
