@@ -13,6 +13,7 @@
  *                          ActionBuffer.reset            env/sim/weight_buffer.py:46-50
  *   pmrl_env_step       <- TradingEnv.step               env/sim/trading_env.py:44-105
  *   pmrl_env_step_host  <- the same call with CPU tensors train/on_policy.py:64-65
+ *   pmrl_price_relatives<- y = close / close.shift(1)        data/instrument.py:79
  *                          ActionBuffer.update/get_last  env/sim/weight_buffer.py:13-30
  *                          ActionBuffer.get_all          env/sim/weight_buffer.py:32-44
  *                          Reward.get_reward & variants  env/reward.py:15-31
@@ -51,7 +52,7 @@
 extern "C" {
 #endif
 
-#define PMRL_ABI_VERSION 1
+#define PMRL_ABI_VERSION 2   /* 2: PmrlTables.y_tm, pmrl_env_step_host, pmrl_price_relatives */
 
 /* error codes (negative) */
 #define PMRL_E_ARG        (-1)   /* null pointer / bad enum */
@@ -89,6 +90,8 @@ typedef struct PmrlEnvCfg {
 typedef struct PmrlTables {
     const float* close_tm;     /* [T, A] or NULL when y is supplied externally */
     const float* feat_am;      /* [A, T, F-1] or NULL when obs_mode != PMRL_OBS_FULL */
+    const float* y_tm;         /* [T, A] price relatives close[t]/close[t-1] from pmrl_price_relatives, or NULL → the step
+                                  kernel divides the two close rows itself (same bits, one IEEE division per asset-step more) */
 } PmrlTables;
 
 typedef struct PmrlEnvState {
@@ -165,6 +168,15 @@ int pmrl_env_step_host(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlE
                        const float* actions_host, float* actions_stage,
                        float* reward, uint8_t* done, float* reward_host, uint8_t* done_host,
                        float* obs, int32_t obs_mode, double* stats, int32_t slices, void* stream);
+
+/* y_tm[t, a] = close_tm[t, a] / close_tm[t-1, a] (data/instrument.py:79: `close / close.shift(1)`), row 0 = 1.
+ * Optional companion of close_tm for PmrlTables.y_tm.  close_tm, y_tm [T, A]. */
+int pmrl_price_relatives(const float* close_tm, int32_t T, int32_t A, float* y_tm, void* stream);
+
+/* Self-test of the kernels' shared-divisor quotient against IEEE division: den[i / 32] divides num[i] (n numerators,
+ * ceil(n/32) divisors, device pointers); out[0] += pairs whose bits differ, out[1] += pairs tested (operands outside
+ * the range in which the kernels use the shared-divisor form are skipped).  out: uint64[2] device, caller-zeroed. */
+int pmrl_selftest_division(const float* num, const float* den, int64_t n, uint64_t* out, void* stream);
 
 /* Materialise obs for the current state without stepping (obs_mode FULL or WEIGHTS). */
 int pmrl_obs_build(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,

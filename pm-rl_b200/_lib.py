@@ -24,7 +24,7 @@ class PmrlEnvCfg(C.Structure):
 
 
 class PmrlTables(C.Structure):
-    _fields_ = [("close_tm", c_void_p), ("feat_am", c_void_p)]
+    _fields_ = [("close_tm", c_void_p), ("feat_am", c_void_p), ("y_tm", c_void_p)]
 
 
 class PmrlEnvState(C.Structure):
@@ -43,6 +43,8 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, i32, c_void_p, c_void_p]),
     "pmrl_env_step_host": (C.c_int, [P(PmrlEnvCfg), P(PmrlTables), P(PmrlEnvState), c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, i32, c_void_p, i32, c_void_p]),
+    "pmrl_price_relatives": (C.c_int, [c_void_p, i32, i32, c_void_p, c_void_p]),
+    "pmrl_selftest_division": (C.c_int, [c_void_p, c_void_p, C.c_int64, c_void_p, c_void_p]),
     "pmrl_obs_build": (C.c_int, [P(PmrlEnvCfg), P(PmrlTables), P(PmrlEnvState), c_void_p, i32, c_void_p]),
     "pmrl_ffd_weights": (C.c_int, [c_void_p, i32, i32, f32, c_void_p, c_void_p, c_void_p]),
     "pmrl_ffd_transform": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, i32, i32, i32, c_void_p, c_void_p]),
@@ -89,7 +91,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here means header and library diverged
         fn.restype = res
         fn.argtypes = args
-    if lib.pmrl_abi_version() != 1:
+    if lib.pmrl_abi_version() != 2:
         raise PmrlError("libpmrl_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -285,7 +285,7 @@ static int fill_params(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlE
     const double c = (double)cfg->commission;
     p.mu0 = (float)(1.0 - 2.0 * c + c * c);
     p.c2 = (float)(2.0 * c - c * c);
-    if (tbl) { p.close_tm = tbl->close_tm; p.feat_am = tbl->feat_am; }
+    if (tbl) { p.close_tm = tbl->close_tm; p.feat_am = tbl->feat_am; p.y_tm = tbl->y_tm; }
     p.value = st->value; p.hist = st->hist; p.idx = st->idx; p.is_full = st->is_full; p.t = st->t;
     p.t0 = st->t0; p.sharpe = st->sharpe; p.ep_return = st->ep_return;
     return 0;
@@ -436,6 +436,48 @@ extern "C" int pmrl_env_reset(const PmrlEnvCfg* cfg, const PmrlTables* tbl, cons
     return 0;
 }
 
+// y_tm[t, a] = close_tm[t, a] / close_tm[t-1, a] (data/instrument.py:79), row 0 = 1.  Same IEEE division the step kernels
+// perform when no y table is given, done once per table instead of once per env-step.
+__global__ void k_price_relatives(const float* __restrict__ close_tm, int T, int A, float* __restrict__ y_tm) {
+    const size_t n = (size_t)T * A;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y_tm[i] = (i < (size_t)A) ? 1.0f : __fdiv_rn(close_tm[i], close_tm[i - A]);
+}
+
+extern "C" int pmrl_price_relatives(const float* close_tm, int32_t T, int32_t A, float* y_tm, void* stream) {
+    if (!close_tm || !y_tm) return pmrl_fail(PMRL_E_ARG, "price_relatives: null pointer");
+    if (T < 1 || A < 1) return pmrl_fail(PMRL_E_SHAPE, "price_relatives: T >= 1, A >= 1 required");
+    const size_t n = (size_t)T * A;
+    const size_t want = (n + 255) / 256, cap = (size_t)pmrl_sm_count() * 16;
+    k_price_relatives<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(close_tm, T, A, y_tm);
+    return pmrl_check_launch("k_price_relatives");
+}
+
+// Bit-for-bit comparison of the shared-reciprocal quotient (pmrl_device.cuh: unidiv) with IEEE division on caller-supplied
+// operands: den[i / 32] divides num[i]; pairs outside the range the kernels accept are skipped and counted separately.
+__global__ void k_selftest_division(const float* __restrict__ num, const float* __restrict__ den, long long n,
+                                    unsigned long long* __restrict__ out /* [2]: mismatches, pairs tested */) {
+    unsigned long long bad = 0, tested = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float a = num[i], b = den[i >> 5];
+        if (!unidiv_in_range(b) || !(a == 0.0f || unidiv_in_range(a))) continue;
+        const UniDiv d = unidiv_make(b);
+        const float q = unidiv(a, d), ref = __fdiv_rn(a, b);
+        ++tested;
+        if (__float_as_uint(q) != __float_as_uint(ref)) ++bad;
+    }
+    if (bad) atomicAdd(out, bad);
+    if (tested) atomicAdd(out + 1, tested);
+}
+
+extern "C" int pmrl_selftest_division(const float* num, const float* den, int64_t n, uint64_t* out, void* stream) {
+    if (!num || !den || !out) return pmrl_fail(PMRL_E_ARG, "selftest_division: null pointer");
+    if (n < 0) return pmrl_fail(PMRL_E_SHAPE, "selftest_division: n < 0");
+    if (n == 0) return 0;
+    k_selftest_division<<<pmrl_sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(num, den, (long long)n, (unsigned long long*)out);
+    return pmrl_check_launch("k_selftest_division");
+}
+
 extern "C" int pmrl_obs_build(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
                               float* obs, int32_t obs_mode, void* stream) {
     StepParams p;
@@ -454,9 +496,9 @@ extern "C" int pmrl_env_step(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const
     if (int rc = fill_params(cfg, tbl, st, p)) return rc;
     if (!actions || !reward || !done) return pmrl_fail(PMRL_E_ARG, "actions/reward/done is NULL");
     if (!y_ext) {
-        if (!p.close_tm) return pmrl_fail(PMRL_E_ARG, "need close_tm or y_ext");
-        if (!p.t0) return pmrl_fail(PMRL_E_ARG, "t0 is NULL but y comes from close_tm");
-        if (p.episode_len <= 0) return pmrl_fail(PMRL_E_SHAPE, "episode_len must be > 0 when y comes from close_tm");
+        if (!p.close_tm && !p.y_tm) return pmrl_fail(PMRL_E_ARG, "need close_tm, y_tm or y_ext");
+        if (!p.t0) return pmrl_fail(PMRL_E_ARG, "t0 is NULL but y comes from the price table");
+        if (p.episode_len <= 0) return pmrl_fail(PMRL_E_SHAPE, "episode_len must be > 0 when y comes from the price table");
     }
     if (cfg->reward_mode < 0 || cfg->reward_mode > PMRL_REWARD_SHARPE) return pmrl_fail(PMRL_E_ARG, "bad reward_mode");
     if (cfg->reward_mode == PMRL_REWARD_SHARPE && !p.sharpe) return pmrl_fail(PMRL_E_ARG, "sharpe state is NULL");

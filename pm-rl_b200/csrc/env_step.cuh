@@ -77,7 +77,14 @@ __device__ __forceinline__ void env_load_vectors(const StepParams& p, int e, int
         for (int j = 0; j < NPL; ++j) {
             const int a = lane + 32 * j;
             v.c1[j] = (a < A) ? ld_once(p.y_ext + eA + a, pol_once) : 0.0f;
-            v.c0[j] = 1.0f;
+        }
+    } else if (p.y_tm) {                                         // precomputed price relatives: one load, no division
+        const uint64_t pol_keep = l2_policy_evict_last();
+        const float* __restrict__ r1 = p.y_tm + (size_t)(s.t0e + s.k + W) * A;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int a = lane + 32 * j;
+            v.c1[j] = (a < A) ? ld_keep(r1 + a, pol_keep) : 0.0f;
         }
     } else {
         const uint64_t pol_keep = l2_policy_evict_last();
@@ -164,8 +171,16 @@ __device__ __forceinline__ void env_compute_store(const StepParams& p, int e, in
             se = __fadd_rn(se, v.a[j]);
         }
         se = warp_sum(se);
+        // e_j / Σe over one divisor.  min_j e_j = exp(min_j a_j − mx) and max_j e_j ≤ Σe, so the shared-reciprocal form is
+        // exact when the smallest raw score is above −41 (e^-41 > 2^-60) and Σe is in range; NaNs fail both tests.
+        if (__fsub_rn(mn, mx) >= -41.0f && se >= kUniDivLo && se <= kUniDivHi) {
+            const UniDiv d = unidiv_make(se);
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) v.a[j] = __fdiv_rn(v.a[j], se);
+            for (int j = 0; j < NPL; ++j) v.a[j] = unidiv(v.a[j], d);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) v.a[j] = __fdiv_rn(v.a[j], se);
+        }
     }
 
     // ---- transaction remainder factor mu (trading_env.py:67-75; upstream PGPortfolio relu form) ----
@@ -178,14 +193,15 @@ __device__ __forceinline__ void env_compute_store(const StepParams& p, int e, in
         const float cw = __fmul_rn(c, wl0);
         float mu_last = 1.0f, mu = p.mu0;
         int it = 0;
+        // the sum runs over assets i >= 1: asset 0 (cash) is taken out by a −inf previous weight, the slots beyond A hold
+        // wl = w = 0 and contribute relu(0) = 0 — no per-slot guard inside the iteration
+        if (lane == 0) v.wl[0] = -INFINITY;
         while (fabsf(__fsub_rn(mu, mu_last)) > 1e-10f && it < p.mu_max_iter) {
             mu_last = mu;
             float part = 0.0f;
 #pragma unroll
-            for (int j = 0; j < NPL; ++j) {
-                const int a = lane + 32 * j;
-                if (a >= 1 && a < A) part = __fadd_rn(part, fmaxf(__fsub_rn(v.wl[j], __fmul_rn(mu, v.a[j])), 0.0f));
-            }
+            for (int j = 0; j < NPL; ++j)
+                part = __fadd_rn(part, fmaxf(__fsub_rn(v.wl[j], __fmul_rn(mu, v.a[j])), 0.0f));
             part = warp_sum(part);
             const float numer = __fsub_rn(__fsub_rn(1.0f, cw), __fmul_rn(p.c2, part));
             mu = __fdiv_rn(numer, denom);
@@ -195,16 +211,39 @@ __device__ __forceinline__ void env_compute_store(const StepParams& p, int e, in
     }
 
     // ---- value, drift, return (trading_env.py:78-90); y = close_t / close_{t-1} (instrument.py:79) ----
-    float part = 0.0f;
+    float part = 0.0f, lo = INFINITY, hi = 0.0f;           // lo/hi: range of |port_j| for the shared-reciprocal division
+    if (p.y_ext || p.y_tm) {                                // c1 already is the price relative
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            v.a[j] = (lane + 32 * j < A) ? __fmul_rn(V, __fmul_rn(v.a[j], v.c1[j])) : 0.0f;
+            part = __fadd_rn(part, v.a[j]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const float y = __fdiv_rn(v.c1[j], v.c0[j]);
+            v.a[j] = (lane + 32 * j < A) ? __fmul_rn(V, __fmul_rn(v.a[j], y)) : 0.0f;
+            part = __fadd_rn(part, v.a[j]);
+        }
+    }
 #pragma unroll
     for (int j = 0; j < NPL; ++j) {
-        const float y = __fdiv_rn(v.c1[j], v.c0[j]);
-        v.a[j] = (lane + 32 * j < A) ? __fmul_rn(V, __fmul_rn(v.a[j], y)) : 0.0f;
-        part = __fadd_rn(part, v.a[j]);
+        const float ap = (lane + 32 * j < A) ? fabsf(v.a[j]) : 1.0f;
+        lo = fminf(lo, ap);
+        hi = fmaxf(hi, ap);
     }
     const float Vn = warp_sum(part);
+    // w' = port / V' (trading_env.py:83): one divisor for the whole env.  A zero, denormal, huge or NaN holding anywhere in
+    // the env (fminf/fmaxf drop NaNs, so those are caught through V') sends the warp down the plain IEEE division.
+    const bool uni = __all_sync(PMRL_FULL_MASK, lo >= kUniDivLo && hi <= kUniDivHi) && unidiv_in_range(Vn);
+    if (uni) {
+        const UniDiv d = unidiv_make(Vn);
 #pragma unroll
-    for (int j = 0; j < NPL; ++j) v.a[j] = __fdiv_rn(v.a[j], Vn);
+        for (int j = 0; j < NPL; ++j) v.a[j] = unidiv(v.a[j], d);
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) v.a[j] = __fdiv_rn(v.a[j], Vn);
+    }
     const float ret = __fdiv_rn(Vn, V);
 
     // ---- ring write (weight_buffer.py:21-26) ----

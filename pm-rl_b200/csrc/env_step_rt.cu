@@ -198,15 +198,30 @@ static int launch_rt_w(StepParams& p, size_t smem, int grid, cudaStream_t s) {
     return launch_rt_t<NPL, HASC, 0>(p, smem, grid, s);
 }
 
+// Envs per group for a batch of E envs on `slots` persistent CTAs.  A CTA's time is (rounds it runs) x (envs per group +
+// about one env-time of per-group overhead: barriers and the un-overlapped step phase), and every CTA waits for the
+// slowest, so minimise ceil(ceil(E/g)/slots) * (g + 1).  Measured on 4,096 x 50 (config 2): g = 7 → 2 full rounds,
+// 58.6 us; the former power-of-two choice g = 4 → 3.46 → 4 rounds, 67.2 us.  Large batches end up at kRtGroup.
+static int pick_group(int E, int slots) {
+    int best = 1;
+    long best_cost = -1;
+    for (int g = kRtGroup; g >= 1; --g) {
+        const long n = (E + g - 1) / g;
+        const long rounds = (n + slots - 1) / slots;
+        const long cost = rounds * (g + 1);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = g; }
+    }
+    return best;
+}
+
 int pmrl_launch_step_obs_rt(StepParams& p, int npl, int group, int ctas_per_sm, cudaStream_t s) {
     if (p.F != 5 || p.W > 64 || npl > 4 || p.A < 32) return -100;     // A >= 32: a 32-row tile spans at most two envs
     if (((size_t)p.W * p.A) % 4 != 0 || ((uintptr_t)p.hist) % 16 != 0) return -100;   // every env's ring 16-byte aligned
     if ((size_t)p.A * p.T >= (1u << 31) || p.A >= 65536) return -100;
     const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : 2;
     const int slots = pmrl_sm_count() * per_sm;
-    int G = group > 0 ? group : kRtGroup;
+    int G = group > 0 ? group : pick_group(p.E, slots);
     if (G > kRtGroup) G = kRtGroup;
-    while (G > 1 && (p.E + G - 1) / G < 2 * slots) G >>= 1;
     p.group_envs = G;
     p.tile_assets = 32;
     const size_t smem = (size_t)2 * 32 * p.W * 5 * 4 + (size_t)2 * p.W * p.A * 4 + (size_t)G * p.A * 8;

@@ -30,7 +30,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} is declared in include/pmrl_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared_symbols(), "ctypes signature table and header diverged"
-    assert _lib.load().pmrl_abi_version() == 1
+    assert _lib.load().pmrl_abi_version() == 2
 
 
 def test_argument_validation_needs_no_gpu():

@@ -109,7 +109,8 @@ DEFAULT_TM = 0
 # fast fill, generic fill, warp-specialised TMA pipeline with 2..6 stages (tma=1), ring-through-TMA variant (tma=2), tensor-map TMA variant (tma=3))
 # and the two-kernel path
 VARIANTS = [(1, 0, 0, 0, 1), (1, 0, 3, 0, 1), (1, 8, 3, 0, 0), (1, 32, 1, 0, 0), (0, 0, 0, 0, 1),
-            (1, 0, 0, 1, 4), (1, 0, 2, 1, 2), (1, 0, 8, 1, 6), (1, 0, 0, 2, 1), (1, 0, 3, 2, 1), (1, 0, 0, 3, 1), (1, 0, 3, 3, 1)]
+            (1, 0, 0, 1, 4), (1, 0, 2, 1, 2), (1, 0, 8, 1, 6), (1, 0, 0, 2, 1), (1, 0, 3, 2, 1), (1, 0, 5, 2, 1), (1, 0, 7, 2, 1),
+            (1, 0, 0, 3, 1), (1, 0, 3, 3, 1)]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -143,6 +144,25 @@ def test_table_driven_step_and_obs_vs_oracle(A, W, F, E, variant, tuning):
         util.assert_rewards_close(r.cpu().numpy(), r_o, f"step {s}")
         compare_state(gpu, ora, f"step {s}")
         if s < 4 or s % 5 == 0 or (W - 3 <= s % (L + 1) <= W + 2) or s % (L + 1) in (L - 1, L, 0):
+            compare_obs(obs, ora, f"obs @ {s}")
+
+
+@pytest.mark.parametrize("E", [300, 2048, 2500])
+def test_midsize_batches_use_wave_sized_groups(E):
+    """Batches of a few CTA rounds: the RT launcher sizes its env groups to fill whole rounds (2, 7, 8 envs here) and the
+    last group is ragged."""
+    A, W, L = 40, 8, 12
+    gpu, ora = make_pair(E, A, W, 5, episode_len=L)
+    g = torch.Generator().manual_seed(7)
+    obs = gpu.reset()
+    for s in range(L + 3):
+        act = torch.randn(E, A, generator=g)
+        obs, r, done = gpu.step(act.cuda())
+        r_o, d_o = ora.step(act.numpy())
+        np.testing.assert_array_equal(done.cpu().numpy(), d_o, err_msg=f"done @ {s}")
+        util.assert_rewards_close(r.cpu().numpy(), r_o, f"step {s}")
+        if s in (0, 5, W - 1, W, L - 1, L, L + 2):
+            compare_state(gpu, ora, f"step {s}")
             compare_obs(obs, ora, f"obs @ {s}")
 
 
@@ -432,3 +452,76 @@ def test_random_shape_fuzz(seed):
         if want_obs:
             compare_obs(obs, ora, f"obs @ {s}")
     compare_state(gpu, ora, "end")
+
+
+@pytest.mark.parametrize("A,W,commission,obs", [(100, 50, 0.0, True), (500, 50, 0.0025, False), (11, 8, 0.02, True), (50, 50, 0.0, False)])
+def test_price_relatives_table_gives_the_same_bits_as_the_in_kernel_division(A, W, commission, obs):
+    """PmrlTables.y_tm (close[t]/close[t-1] computed once per table) replaces one IEEE division per asset-step: every
+    float of the state, the reward and the obs must be bit-identical with and without it."""
+    pmrl, synth, Env = _mods()
+    E, L = 40, 30
+    tbl = synth.gbm_ohlc(W + L + 40, A, 77)
+    t0 = synth.episode_offsets(E, W + L + 40, W, L)
+    cfg = pmrl.EnvConfig(num_envs=E, num_assets=A, window_size=W, commission=commission, episode_len=L)
+    with_tbl = Env(cfg, prices=tbl, t0=t0)
+    without = Env(cfg, prices=tbl, t0=t0, price_relatives_table=False)
+    assert with_tbl.y_tm is not None and without.y_tm is None
+    ref_y = torch.ones_like(with_tbl.close_tm); ref_y[1:] = with_tbl.close_tm[1:] / with_tbl.close_tm[:-1]
+    assert torch.equal(with_tbl.y_tm, ref_y)
+    g = torch.Generator().manual_seed(5)
+    with_tbl.reset(obs=obs); without.reset(obs=obs)
+    for s in range(L + 3):
+        act = torch.randn(E, A, generator=g).cuda()
+        if s % 4 == 1:
+            act = torch.softmax(act, dim=1)
+        o1, r1, d1 = with_tbl.step(act, obs=obs)
+        o2, r2, d2 = without.step(act, obs=obs)
+        assert torch.equal(r1, r2) and torch.equal(d1, d2), f"step {s}"
+        assert torch.equal(with_tbl.value, without.value) and torch.equal(with_tbl.hist, without.hist), f"step {s}"
+        if obs:
+            assert torch.equal(o1, o2), f"step {s}"
+
+
+def test_shared_divisor_quotients_equal_ieee_division_bit_for_bit():
+    """The kernels divide a whole env by one divisor (softmax sum, new portfolio value) through a shared refined
+    reciprocal; pmrl_selftest_division compares that quotient with IEEE division on the same operands."""
+    from pmrl_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(2024)
+    n = 1 << 25
+
+    def run(num, den):
+        out = torch.zeros(2, dtype=torch.int64, device="cuda")
+        _lib.check(lib.pmrl_selftest_division(num.data_ptr(), den.data_ptr(), num.numel(), out.data_ptr(), _lib.current_stream()), "selftest")
+        bad, tested = out.cpu().tolist()
+        return bad, tested
+
+    def rand_float(k, lo_exp, hi_exp):                        # random sign-less mantissa, exponent uniform in [lo, hi)
+        mant = torch.randint(0, 1 << 23, (k,), generator=g, device="cuda", dtype=torch.int32)
+        ex = torch.randint(lo_exp + 127, hi_exp + 127, (k,), generator=g, device="cuda", dtype=torch.int32)
+        return ((ex << 23) | mant).view(torch.float32)
+
+    # (1) the whole accepted range, both signs
+    num = rand_float(n, -60, 60) * (torch.randint(0, 2, (n,), generator=g, device="cuda") * 2 - 1).float()
+    den = rand_float(n // 32, -60, 60)
+    bad, tested = run(num, den)
+    assert bad == 0 and tested == n
+    # (2) softmax-like: numerators e^x, divisor their sum; (3) drift-like: holdings / their sum
+    x = torch.randn(n // 32, 32, generator=g, device="cuda") * 3.0
+    e = torch.exp(x)
+    bad, tested = run(e.reshape(-1), e.sum(dim=1))
+    assert bad == 0 and tested == n
+    w = torch.softmax(x, dim=1) * 25000.0 * (1.0 + 0.02 * torch.randn(n // 32, 32, generator=g, device="cuda"))
+    bad, tested = run(w.reshape(-1).contiguous(), w.sum(dim=1))
+    assert bad == 0 and tested == n
+    # (4) mantissa corner cases: all-ones / all-zeros / one-bit mantissas against each other, zeros among the numerators
+    corner = torch.tensor([0x3F800000, 0x3FFFFFFF, 0x3F800001, 0x3FC00000, 0x3FFFFFFE, 0x40490FDB, 0x3EAAAAAB, 0x00000000],
+                          dtype=torch.int32, device="cuda").view(torch.float32)
+    num = corner.repeat(4 * 1024)                             # 32,768 numerators, 32 per divisor
+    den = rand_float(num.numel() // 32, -3, 3)
+    den[:8] = corner[:8].abs().clamp_min(1.0)
+    bad, tested = run(num, den)
+    assert bad == 0 and tested == num.numel()
+    # out-of-range operands are skipped, not mis-divided
+    bad, tested = run(torch.full((64,), 1e-30, device="cuda"), torch.ones(2, device="cuda"))
+    assert (bad, tested) == (0, 0)

@@ -12,7 +12,7 @@ from pmrl_b200.env import BatchedTradingEnv
 
 
 def main():
-    E, A, W = 131072, 100, 50
+    E, A, W = (int(sys.argv[1]) if len(sys.argv) > 1 else 131072), (int(sys.argv[2]) if len(sys.argv) > 2 else 100), 50
     tbl = synth.gbm_ohlc(4096, A)
     cfg = pmrl_b200.EnvConfig(num_envs=E, num_assets=A, window_size=W, episode_len=1000)
     env = BatchedTradingEnv(cfg, prices=tbl, t0=synth.episode_offsets(E, 4096, W, 1000), device="cuda", collect_stats=True)
