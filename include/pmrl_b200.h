@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define PMRL_ABI_VERSION 2   /* 2: PmrlTables.y_tm, pmrl_env_step_host, pmrl_price_relatives */
+#define PMRL_ABI_VERSION 2   /* 2: PmrlTables carries the price-relative table; pmrl_env_step_host, pmrl_price_relatives */
 
 /* error codes (negative) */
 #define PMRL_E_ARG        (-1)   /* null pointer / bad enum */
@@ -88,10 +88,9 @@ typedef struct PmrlEnvCfg {
 } PmrlEnvCfg;
 
 typedef struct PmrlTables {
-    const float* close_tm;     /* [T, A] or NULL when y is supplied externally */
+    const float* y_tm;         /* [T, A] price relatives y[t] = close[t] / close[t-1] (row 0 = 1) built by
+                                  pmrl_price_relatives from the time-major close plane, or NULL when y is supplied externally */
     const float* feat_am;      /* [A, T, F-1] or NULL when obs_mode != PMRL_OBS_FULL */
-    const float* y_tm;         /* [T, A] price relatives close[t]/close[t-1] from pmrl_price_relatives, or NULL → the step
-                                  kernel divides the two close rows itself (same bits, one IEEE division per asset-step more) */
 } PmrlTables;
 
 typedef struct PmrlEnvState {
@@ -170,7 +169,8 @@ int pmrl_env_step_host(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlE
                        float* obs, int32_t obs_mode, double* stats, int32_t slices, void* stream);
 
 /* y_tm[t, a] = close_tm[t, a] / close_tm[t-1, a] (data/instrument.py:79: `close / close.shift(1)`), row 0 = 1.
- * Optional companion of close_tm for PmrlTables.y_tm.  close_tm, y_tm [T, A]. */
+ * Builds PmrlTables.y_tm: the reference divides once per loader item on the host, the step kernels read the quotient.
+ * close_tm, y_tm [T, A]; the two must not alias (row t reads close row t-1). */
 int pmrl_price_relatives(const float* close_tm, int32_t T, int32_t A, float* y_tm, void* stream);
 
 /* Self-test of the kernels' shared-divisor quotient against IEEE division: den[i / 32] divides num[i] (n numerators,

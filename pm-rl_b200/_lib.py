@@ -24,7 +24,7 @@ class PmrlEnvCfg(C.Structure):
 
 
 class PmrlTables(C.Structure):
-    _fields_ = [("close_tm", c_void_p), ("feat_am", c_void_p), ("y_tm", c_void_p)]
+    _fields_ = [("y_tm", c_void_p), ("feat_am", c_void_p)]
 
 
 class PmrlEnvState(C.Structure):

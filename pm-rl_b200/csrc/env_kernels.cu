@@ -48,9 +48,20 @@ __global__ void __launch_bounds__(kStepThreads) k_env_step(const StepParams p) {
             s0 = s1; s1 = s2; v0 = v1;
         }
     } else {
-        for (int e = gw; e < p.E; e += nw) {
+        // wide envs (NPL >= 8): no registers for a second env's vectors.  Keep the scalars of the next two envs in
+        // registers and pull the next env's DRAM rows into L2 while this one computes: the dependent chain
+        // scalars → row addresses → vectors then costs one L2 hit per env instead of two DRAM round trips.
+        EnvScalars s0, s1, s2;
+        int e = gw;
+        if (e < p.E) env_load_scalars(p, e, s0);
+        if (e + nw < p.E) env_load_scalars(p, e + nw, s1);
+        for (; e < p.E; e += nw) {
             EnvVectors<NPL, HASC> v;
-            env_step_warp<NPL, HASC>(p, e, lane, v, so, acc);
+            if (e + 2 * nw < p.E) env_load_scalars(p, e + 2 * nw, s2);
+            env_load_vectors<NPL, HASC>(p, e, lane, s0, v);
+            if (e + nw < p.E) env_prefetch_vectors<HASC>(p, e + nw, lane, s1);
+            env_compute_store<NPL, HASC>(p, e, lane, s0, v, so, acc);
+            s0 = s1; s1 = s2;
         }
     }
     if (p.stats) stats_flush_block(p.stats, s_stats, kStepWarps);
@@ -285,7 +296,7 @@ static int fill_params(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlE
     const double c = (double)cfg->commission;
     p.mu0 = (float)(1.0 - 2.0 * c + c * c);
     p.c2 = (float)(2.0 * c - c * c);
-    if (tbl) { p.close_tm = tbl->close_tm; p.feat_am = tbl->feat_am; p.y_tm = tbl->y_tm; }
+    if (tbl) { p.y_tm = tbl->y_tm; p.feat_am = tbl->feat_am; }
     p.value = st->value; p.hist = st->hist; p.idx = st->idx; p.is_full = st->is_full; p.t = st->t;
     p.t0 = st->t0; p.sharpe = st->sharpe; p.ep_return = st->ep_return;
     return 0;
@@ -436,8 +447,8 @@ extern "C" int pmrl_env_reset(const PmrlEnvCfg* cfg, const PmrlTables* tbl, cons
     return 0;
 }
 
-// y_tm[t, a] = close_tm[t, a] / close_tm[t-1, a] (data/instrument.py:79), row 0 = 1.  Same IEEE division the step kernels
-// perform when no y table is given, done once per table instead of once per env-step.
+// y_tm[t, a] = close_tm[t, a] / close_tm[t-1, a] (data/instrument.py:79), row 0 = 1: the IEEE division of the reference,
+// done once per table instead of once per env-step.
 __global__ void k_price_relatives(const float* __restrict__ close_tm, int T, int A, float* __restrict__ y_tm) {
     const size_t n = (size_t)T * A;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -496,7 +507,7 @@ extern "C" int pmrl_env_step(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const
     if (int rc = fill_params(cfg, tbl, st, p)) return rc;
     if (!actions || !reward || !done) return pmrl_fail(PMRL_E_ARG, "actions/reward/done is NULL");
     if (!y_ext) {
-        if (!p.close_tm && !p.y_tm) return pmrl_fail(PMRL_E_ARG, "need close_tm, y_tm or y_ext");
+        if (!p.y_tm) return pmrl_fail(PMRL_E_ARG, "need y_tm (pmrl_price_relatives) or y_ext");
         if (!p.t0) return pmrl_fail(PMRL_E_ARG, "t0 is NULL but y comes from the price table");
         if (p.episode_len <= 0) return pmrl_fail(PMRL_E_SHAPE, "episode_len must be > 0 when y comes from the price table");
     }

@@ -4,7 +4,7 @@
 //   TradingEnv.step            env/sim/trading_env.py:54-100
 //   ActionBuffer.update/get_last  env/sim/weight_buffer.py:13-30
 //   Reward.*                   env/reward.py:15-31
-//   y_t = close_t / close_{t-1}   data/instrument.py:79
+//   y_t = close_t / close_{t-1}   data/instrument.py:79  (precomputed once per table: pmrl_price_relatives)
 // keeping the reference association of every fp32 operation (no FMA contraction, IEEE div,
 // expf/logf without fast-math) so values stay within 1e-5 relative over 1,000 compounding steps.
 //
@@ -12,7 +12,7 @@
 // across consecutive envs of a warp (scalars of env n+2, vectors of env n+1 and the arithmetic of env n
 // are in flight together):
 //   env_load_scalars   V, ring pointer, is_full, local step, episode offset
-//   env_load_vectors   raw action, the two close rows (or external y), previous weights (commission only)
+//   env_load_vectors   raw action, the price-relative row (or external y), previous weights (commission only)
 //   env_compute_store  everything else
 #pragma once
 #include "pmrl_device.cuh"
@@ -42,8 +42,7 @@ struct EnvScalars { float V; int i, full, k, t0e; };
 template <int NPL, bool HASC>
 struct EnvVectors {
     float a[NPL];                   // raw action → weights → holdings → w'  (updated in place)
-    float c1[NPL];                  // close_t (or external y)
-    float c0[NPL];                  // close_{t-1}
+    float y[NPL];                   // price relative close_t / close_{t-1} (table row or external)
     float wl[HASC ? NPL : 1];       // previous post-drift weights (only read when commission > 0)
 };
 
@@ -72,45 +71,46 @@ __device__ __forceinline__ void env_load_vectors(const StepParams& p, int e, int
     const int A = p.A, W = p.W;
     const size_t eA = (size_t)e * A;
     const uint64_t pol_once = l2_policy_evict_first();
+    // one validity test per slot shared by the three loads (slots beyond A read as 0 everywhere)
+    const float* __restrict__ act = p.actions + eA;
+    const float* __restrict__ wrow = p.hist;
+    if (HASC) wrow += ((size_t)e * W + (s.i - 1 + W) % W) * A;          // weight_buffer.py:30
     if (p.y_ext) {
+        const float* __restrict__ yrow = p.y_ext + eA;
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
             const int a = lane + 32 * j;
-            v.c1[j] = (a < A) ? ld_once(p.y_ext + eA + a, pol_once) : 0.0f;
+            const bool ok = a < A;
+            v.a[j] = ok ? ld_once(act + a, pol_once) : 0.0f;
+            v.y[j] = ok ? ld_once(yrow + a, pol_once) : 0.0f;
+            if (HASC) v.wl[j] = ok ? wrow[a] : 0.0f;
         }
-    } else if (p.y_tm) {                                         // precomputed price relatives: one load, no division
+    } else {                                                     // row t0 + k_new + W - 1: last row of the new window
         const uint64_t pol_keep = l2_policy_evict_last();
-        const float* __restrict__ r1 = p.y_tm + (size_t)(s.t0e + s.k + W) * A;
+        const float* __restrict__ yrow = p.y_tm + (size_t)(s.t0e + s.k + W) * A;
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
             const int a = lane + 32 * j;
-            v.c1[j] = (a < A) ? ld_keep(r1 + a, pol_keep) : 0.0f;
-        }
-    } else {
-        const uint64_t pol_keep = l2_policy_evict_last();
-        const size_t row = (size_t)(s.t0e + s.k + W);            // row t0 + k_new + W - 1: last row of the new window
-        const float* __restrict__ r1 = p.close_tm + row * A;
-        const float* __restrict__ r0 = r1 - A;
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-            const int a = lane + 32 * j;
-            v.c1[j] = (a < A) ? ld_keep(r1 + a, pol_keep) : 0.0f;
-            v.c0[j] = (a < A) ? ld_keep(r0 + a, pol_keep) : 1.0f;
+            const bool ok = a < A;
+            v.a[j] = ok ? ld_once(act + a, pol_once) : 0.0f;
+            v.y[j] = ok ? ld_keep(yrow + a, pol_keep) : 0.0f;
+            if (HASC) v.wl[j] = ok ? wrow[a] : 0.0f;
         }
     }
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-        const int a = lane + 32 * j;
-        v.a[j] = (a < A) ? ld_once(p.actions + eA + a, pol_once) : 0.0f;
-    }
+}
+
+// Pull the DRAM-resident rows env e will read (its raw action, and its previous weights when commission > 0) into L2
+// one env ahead of the warp, without holding registers for them: one 128-byte line per lane.  The price-relative row
+// lives in the L2-resident table already.
+template <bool HASC>
+__device__ __forceinline__ void env_prefetch_vectors(const StepParams& p, int e, int lane, const EnvScalars& s) {
+    if (env_needs_reset(p, s)) return;
+    const int A = p.A;
+    for (int a = lane * 32; a < A; a += 32 * 32) prefetch_l2(p.actions + (size_t)e * A + a);
     if (HASC) {
-        const int last_slot = (s.i - 1 + W) % W;                 // weight_buffer.py:30
-        const float* __restrict__ wrow = p.hist + ((size_t)e * W + last_slot) * A;
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-            const int a = lane + 32 * j;
-            v.wl[j] = (a < A) ? wrow[a] : 0.0f;
-        }
+        const int last_slot = (s.i - 1 + p.W) % p.W;
+        const float* __restrict__ wrow = p.hist + ((size_t)e * p.W + last_slot) * A;
+        for (int a = lane * 32; a < A; a += 32 * 32) prefetch_l2(wrow + a);
     }
 }
 
@@ -145,11 +145,11 @@ __device__ __forceinline__ void env_compute_store(const StepParams& p, int e, in
     const int k_new = sc.k + 1;
 
     // ---- normalise (trading_env.py:58-60; quirks Q1-Q3) ----
+    // slots beyond A hold 0: neutral for the sum, and for the minimum too, which is only ever compared with 0 (has_neg)
+    // and with the −41 bound of the shared-reciprocal softmax below (a smaller minimum only makes that test stricter)
     float s = 0.0f, mn = INFINITY;
 #pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-        if (lane + 32 * j < A) { s = __fadd_rn(s, v.a[j]); mn = nanmin(mn, v.a[j]); }
-    }
+    for (int j = 0; j < NPL; ++j) { s = __fadd_rn(s, v.a[j]); mn = nanmin(mn, v.a[j]); }
     s = warp_sum(s);
     mn = warp_min_nan(mn);
     const bool strict = (p.flags & PMRL_FLAG_STRICT_REFERENCE) != 0;
@@ -210,21 +210,12 @@ __device__ __forceinline__ void env_compute_store(const StepParams& p, int e, in
         V = __fmul_rn(mu, V);                                    // trading_env.py:75
     }
 
-    // ---- value, drift, return (trading_env.py:78-90); y = close_t / close_{t-1} (instrument.py:79) ----
+    // ---- value, drift, return (trading_env.py:78-90) ----
     float part = 0.0f, lo = INFINITY, hi = 0.0f;           // lo/hi: range of |port_j| for the shared-reciprocal division
-    if (p.y_ext || p.y_tm) {                                // c1 already is the price relative
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-            v.a[j] = (lane + 32 * j < A) ? __fmul_rn(V, __fmul_rn(v.a[j], v.c1[j])) : 0.0f;
-            part = __fadd_rn(part, v.a[j]);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-            const float y = __fdiv_rn(v.c1[j], v.c0[j]);
-            v.a[j] = (lane + 32 * j < A) ? __fmul_rn(V, __fmul_rn(v.a[j], y)) : 0.0f;
-            part = __fadd_rn(part, v.a[j]);
-        }
+    for (int j = 0; j < NPL; ++j) {
+        v.a[j] = (lane + 32 * j < A) ? __fmul_rn(V, __fmul_rn(v.a[j], v.y[j])) : 0.0f;
+        part = __fadd_rn(part, v.a[j]);
     }
 #pragma unroll
     for (int j = 0; j < NPL; ++j) {

@@ -39,20 +39,16 @@ class BatchedTradingEnv:
                    channel count is F-1); FFD'ed / scaled tables come from `pmrl_b200.features`.
         t0:        [E] int episode offsets into the table (default 0).
         collect_stats: accumulate the PMRL_STAT_* vector on device every step.
-        price_relatives_table: precompute y[t] = close[t] / close[t-1] once per table (same bits as the in-kernel
-                   division it replaces; False keeps the division in the step kernel).
     """
 
     @classmethod
-    def from_tables(cls, cfg: EnvConfig, close_tm, feat_am, t0=None, device=None, collect_stats: bool = False,
-                    price_relatives_table: bool = True):
+    def from_tables(cls, cfg: EnvConfig, close_tm, feat_am, t0=None, device=None, collect_stats: bool = False):
         """Construct from tables already in the kernel layouts (close_tm [T, A], feat_am [A, T, F-1]), e.g. the
         output of `pmrl_b200.features.build_env_tables`."""
-        return cls(cfg, t0=t0, device=device, collect_stats=collect_stats, _packed=(close_tm, feat_am),
-                   price_relatives_table=price_relatives_table)
+        return cls(cfg, t0=t0, device=device, collect_stats=collect_stats, _packed=(close_tm, feat_am))
 
     def __init__(self, cfg: EnvConfig, prices=None, features=None, t0=None, close_channel: int = 3,
-                 device=None, collect_stats: bool = False, _packed=None, price_relatives_table: bool = True):
+                 device=None, collect_stats: bool = False, _packed=None):
         if not torch.cuda.is_available():
             raise _lib.PmrlError("BatchedTradingEnv needs a CUDA device (pmrl_b200 has no CPU fallback)")
         self.lib = _lib.load()
@@ -127,13 +123,13 @@ class BatchedTradingEnv:
         self._c_cfg = _lib.PmrlEnvCfg(E, A, W, F, self.T, cfg.episode_len, cfg.reward_mode, cfg.mu_max_iter,
                                       1 if cfg.strict_reference else 0, cfg.initial_cash, cfg.commission,
                                       cfg.reward_scale, cfg.risk_free_rate)
-        # price relatives y[t] = close[t] / close[t-1] once per table (instrument.py:79) instead of once per env-step
+        # price relatives y[t] = close[t] / close[t-1], once per table (instrument.py:79): the table the step kernels read
         self.y_tm = None
-        if self.close_tm is not None and price_relatives_table:
+        if self.close_tm is not None:
             self.y_tm = torch.empty_like(self.close_tm)
             _lib.check(self.lib.pmrl_price_relatives(self.close_tm.data_ptr(), self.T, A, self.y_tm.data_ptr(),
                                                      _lib.current_stream()), "pmrl_price_relatives")
-        self._c_tbl = _lib.PmrlTables(_lib.ptr(self.close_tm), _lib.ptr(self.feat_am), _lib.ptr(self.y_tm))
+        self._c_tbl = _lib.PmrlTables(_lib.ptr(self.y_tm), _lib.ptr(self.feat_am))
         self._c_st = _lib.PmrlEnvState(_lib.ptr(self.value), _lib.ptr(self.hist), _lib.ptr(self.idx),
                                        _lib.ptr(self.is_full), _lib.ptr(self.t), _lib.ptr(self.t0),
                                        _lib.ptr(self.sharpe), _lib.ptr(self.ep_return))

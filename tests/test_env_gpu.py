@@ -454,32 +454,31 @@ def test_random_shape_fuzz(seed):
     compare_state(gpu, ora, "end")
 
 
-@pytest.mark.parametrize("A,W,commission,obs", [(100, 50, 0.0, True), (500, 50, 0.0025, False), (11, 8, 0.02, True), (50, 50, 0.0, False)])
-def test_price_relatives_table_gives_the_same_bits_as_the_in_kernel_division(A, W, commission, obs):
-    """PmrlTables.y_tm (close[t]/close[t-1] computed once per table) replaces one IEEE division per asset-step: every
-    float of the state, the reward and the obs must be bit-identical with and without it."""
+@pytest.mark.parametrize("A,W,commission", [(100, 50, 0.0), (500, 50, 0.0025), (11, 8, 0.02), (200, 16, 0.0)])
+def test_price_relatives_table_equals_ieee_division_and_the_external_y_path(A, W, commission):
+    """PmrlTables.y_tm is close[t]/close[t-1] divided once per table (pmrl_price_relatives): it must equal the IEEE
+    quotient bit for bit, and stepping from the table must give the same bits as stepping with those y rows supplied
+    externally (the reference's call shape, trading_env.py:44)."""
     pmrl, synth, Env = _mods()
     E, L = 40, 30
-    tbl = synth.gbm_ohlc(W + L + 40, A, 77)
-    t0 = synth.episode_offsets(E, W + L + 40, W, L)
+    T = W + L + 40
+    tbl = synth.gbm_ohlc(T, A, 77)
+    t0 = synth.episode_offsets(E, T, W, L)
     cfg = pmrl.EnvConfig(num_envs=E, num_assets=A, window_size=W, commission=commission, episode_len=L)
-    with_tbl = Env(cfg, prices=tbl, t0=t0)
-    without = Env(cfg, prices=tbl, t0=t0, price_relatives_table=False)
-    assert with_tbl.y_tm is not None and without.y_tm is None
-    ref_y = torch.ones_like(with_tbl.close_tm); ref_y[1:] = with_tbl.close_tm[1:] / with_tbl.close_tm[:-1]
-    assert torch.equal(with_tbl.y_tm, ref_y)
+    tab = Env(cfg, prices=tbl, t0=t0)
+    ref_y = torch.ones_like(tab.close_tm); ref_y[1:] = tab.close_tm[1:] / tab.close_tm[:-1]
+    assert torch.equal(tab.y_tm, ref_y)
+    ext = Env(pmrl.EnvConfig(num_envs=E, num_assets=A, window_size=W, commission=commission, episode_len=0))
     g = torch.Generator().manual_seed(5)
-    with_tbl.reset(obs=obs); without.reset(obs=obs)
-    for s in range(L + 3):
+    rows = t0.cuda().long()
+    for s in range(L):
         act = torch.randn(E, A, generator=g).cuda()
         if s % 4 == 1:
             act = torch.softmax(act, dim=1)
-        o1, r1, d1 = with_tbl.step(act, obs=obs)
-        o2, r2, d2 = without.step(act, obs=obs)
-        assert torch.equal(r1, r2) and torch.equal(d1, d2), f"step {s}"
-        assert torch.equal(with_tbl.value, without.value) and torch.equal(with_tbl.hist, without.hist), f"step {s}"
-        if obs:
-            assert torch.equal(o1, o2), f"step {s}"
+        _, r1, _ = tab.step(act, obs=False)
+        _, r2, _ = ext.step(act, y=ref_y[rows + s + W], obs=False)
+        assert torch.equal(r1, r2), f"step {s}"
+        assert torch.equal(tab.value, ext.value) and torch.equal(tab.hist, ext.hist), f"step {s}"
 
 
 def test_shared_divisor_quotients_equal_ieee_division_bit_for_bit():
