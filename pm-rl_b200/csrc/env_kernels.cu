@@ -25,7 +25,7 @@ constexpr int kObsThreads = 256;
 // ------------------------------------------------------------------------------------------------
 // Mode S: state-only step.
 // ------------------------------------------------------------------------------------------------
-template <int NPL, bool HASC, bool PIPE>
+template <int NPL, bool HASC, bool PIPE, bool TAIL>
 __global__ void __launch_bounds__(kStepThreads) k_env_step(const StepParams p) {
     __shared__ double s_stats[kStepWarps * PMRL_STATS_LEN];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -39,12 +39,12 @@ __global__ void __launch_bounds__(kStepThreads) k_env_step(const StepParams p) {
         EnvScalars s0, s1, s2;
         EnvVectors<NPL, HASC> v0, v1;
         int e = gw;
-        if (e < p.E) { env_load_scalars(p, e, s0); env_load_vectors<NPL, HASC>(p, e, lane, s0, v0); }
+        if (e < p.E) { env_load_scalars(p, e, s0); env_load_vectors<NPL, HASC, TAIL>(p, e, lane, s0, v0); }
         if (e + nw < p.E) env_load_scalars(p, e + nw, s1);
         for (; e < p.E; e += nw) {
             if (e + 2 * nw < p.E) env_load_scalars(p, e + 2 * nw, s2);
-            if (e + nw < p.E) env_load_vectors<NPL, HASC>(p, e + nw, lane, s1, v1);
-            env_compute_store<NPL, HASC>(p, e, lane, s0, v0, so, acc);
+            if (e + nw < p.E) env_load_vectors<NPL, HASC, TAIL>(p, e + nw, lane, s1, v1);
+            env_compute_store<NPL, HASC, TAIL>(p, e, lane, s0, v0, so, acc);
             s0 = s1; s1 = s2; v0 = v1;
         }
     } else {
@@ -58,9 +58,9 @@ __global__ void __launch_bounds__(kStepThreads) k_env_step(const StepParams p) {
         for (; e < p.E; e += nw) {
             EnvVectors<NPL, HASC> v;
             if (e + 2 * nw < p.E) env_load_scalars(p, e + 2 * nw, s2);
-            env_load_vectors<NPL, HASC>(p, e, lane, s0, v);
+            env_load_vectors<NPL, HASC, TAIL>(p, e, lane, s0, v);
             if (e + nw < p.E) env_prefetch_vectors<HASC>(p, e + nw, lane, s1);
-            env_compute_store<NPL, HASC>(p, e, lane, s0, v, so, acc);
+            env_compute_store<NPL, HASC, TAIL>(p, e, lane, s0, v, so, acc);
             s0 = s1; s1 = s2;
         }
     }
@@ -333,7 +333,9 @@ static int launch_step_s(const StepParams& p, cudaStream_t s) {
     constexpr bool PIPE = (NPL <= 4);                 // 3-stage software pipeline while the registers allow it
     const int want = (p.E + kStepWarps - 1) / kStepWarps;
     const int cap = pmrl_sm_count() * 8;
-    k_env_step<NPL, HASC, PIPE><<<want < cap ? want : cap, kStepThreads, 0, s>>>(p);
+    // TAIL: every 32-asset slot row but the last is full → only the last row carries validity guards
+    if (p.A > 32 * (NPL - 1)) k_env_step<NPL, HASC, PIPE, true><<<want < cap ? want : cap, kStepThreads, 0, s>>>(p);
+    else k_env_step<NPL, HASC, PIPE, false><<<want < cap ? want : cap, kStepThreads, 0, s>>>(p);
     return pmrl_check_launch("k_env_step");
 }
 

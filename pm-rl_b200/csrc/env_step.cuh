@@ -46,6 +46,15 @@ struct EnvVectors {
     float wl[HASC ? NPL : 1];       // previous post-drift weights (only read when commission > 0)
 };
 
+// Is asset slot j of this lane a real asset?  With TAIL the caller guarantees A > 32·(NPL−1) — every slot row but the
+// last is full — so the test folds to `true` at compile time for j < NPL−1 and only the last row is guarded
+// (all BASELINE shapes: A = 11, 50, 100, 500 ↔ NPL = 1, 2, 4, 16).
+template <int NPL, bool TAIL>
+__device__ __forceinline__ bool slot_ok(int j, int lane, int A) {
+    if (TAIL && j < NPL - 1) return true;
+    return lane + 32 * j < A;
+}
+
 // Zero the ring of env e and set the all-cash row (weight_buffer.py:46-50).
 __device__ __forceinline__ void ring_reset_warp(float* __restrict__ hist_e, int W, int A, int lane) {
     const int n = W * A;
@@ -64,7 +73,7 @@ __device__ __forceinline__ bool env_needs_reset(const StepParams& p, const EnvSc
     return p.episode_len > 0 && s.k >= p.episode_len;           // train/on_policy.py:60-61
 }
 
-template <int NPL, bool HASC>
+template <int NPL, bool HASC, bool TAIL = false>
 __device__ __forceinline__ void env_load_vectors(const StepParams& p, int e, int lane, const EnvScalars& s,
                                                  EnvVectors<NPL, HASC>& v) {
     if (env_needs_reset(p, s)) return;                           // nothing is read on the auto-reset call
@@ -80,7 +89,7 @@ __device__ __forceinline__ void env_load_vectors(const StepParams& p, int e, int
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
             const int a = lane + 32 * j;
-            const bool ok = a < A;
+            const bool ok = slot_ok<NPL, TAIL>(j, lane, A);
             v.a[j] = ok ? ld_once(act + a, pol_once) : 0.0f;
             v.y[j] = ok ? ld_once(yrow + a, pol_once) : 0.0f;
             if (HASC) v.wl[j] = ok ? wrow[a] : 0.0f;
@@ -91,7 +100,7 @@ __device__ __forceinline__ void env_load_vectors(const StepParams& p, int e, int
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
             const int a = lane + 32 * j;
-            const bool ok = a < A;
+            const bool ok = slot_ok<NPL, TAIL>(j, lane, A);
             v.a[j] = ok ? ld_once(act + a, pol_once) : 0.0f;
             v.y[j] = ok ? ld_keep(yrow + a, pol_keep) : 0.0f;
             if (HASC) v.wl[j] = ok ? wrow[a] : 0.0f;
@@ -115,7 +124,7 @@ __device__ __forceinline__ void env_prefetch_vectors(const StepParams& p, int e,
 }
 
 // On return v.a[] holds w' (the post-drift weights, lane-strided: asset a = lane + 32*j).
-template <int NPL, bool HASC>
+template <int NPL, bool HASC, bool TAIL = false>
 __device__ __forceinline__ void env_compute_store(const StepParams& p, int e, int lane, const EnvScalars& sc,
                                                   EnvVectors<NPL, HASC>& v, StepOut& out,
                                                   double* __restrict__ acc /* smem [10] of this warp */) {
@@ -161,13 +170,13 @@ __device__ __forceinline__ void env_compute_store(const StepParams& p, int e, in
         if (!strict) {                                           // stabilised softmax (agent/pg/pg.py:53)
             mx = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < NPL; ++j) if (lane + 32 * j < A) mx = fmaxf(mx, v.a[j]);
+            for (int j = 0; j < NPL; ++j) if (slot_ok<NPL, TAIL>(j, lane, A)) mx = fmaxf(mx, v.a[j]);
             mx = warp_max(mx);
         }
         float se = 0.0f;
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
-            v.a[j] = (lane + 32 * j < A) ? expf(__fsub_rn(v.a[j], mx)) : 0.0f;
+            v.a[j] = slot_ok<NPL, TAIL>(j, lane, A) ? expf(__fsub_rn(v.a[j], mx)) : 0.0f;
             se = __fadd_rn(se, v.a[j]);
         }
         se = warp_sum(se);
@@ -214,12 +223,12 @@ __device__ __forceinline__ void env_compute_store(const StepParams& p, int e, in
     float part = 0.0f, lo = INFINITY, hi = 0.0f;           // lo/hi: range of |port_j| for the shared-reciprocal division
 #pragma unroll
     for (int j = 0; j < NPL; ++j) {
-        v.a[j] = (lane + 32 * j < A) ? __fmul_rn(V, __fmul_rn(v.a[j], v.y[j])) : 0.0f;
+        v.a[j] = slot_ok<NPL, TAIL>(j, lane, A) ? __fmul_rn(V, __fmul_rn(v.a[j], v.y[j])) : 0.0f;
         part = __fadd_rn(part, v.a[j]);
     }
 #pragma unroll
     for (int j = 0; j < NPL; ++j) {
-        const float ap = (lane + 32 * j < A) ? fabsf(v.a[j]) : 1.0f;
+        const float ap = slot_ok<NPL, TAIL>(j, lane, A) ? fabsf(v.a[j]) : 1.0f;
         lo = fminf(lo, ap);
         hi = fmaxf(hi, ap);
     }
@@ -241,7 +250,7 @@ __device__ __forceinline__ void env_compute_store(const StepParams& p, int e, in
 #pragma unroll
     for (int j = 0; j < NPL; ++j) {
         const int a = lane + 32 * j;
-        if (a < A) hist_e[(size_t)i * A + a] = v.a[j];
+        if (slot_ok<NPL, TAIL>(j, lane, A)) hist_e[(size_t)i * A + a] = v.a[j];
     }
     const int i_new = (i + 1 == W) ? 0 : i + 1;
     if (i_new == 0) full = 1;
