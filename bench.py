@@ -33,6 +33,7 @@ WORKLOADS = {
     "c2_state": (4096, 50, 50, 5, 0.0, False, "BASELINE config 2, state-only step (no obs)"),
     "c3": (65536, 100, 50, 5, 0.0, True, "BASELINE config 3: 65,536 envs x 100 assets, obs materialised"),
     "c5": (262144, 500, 50, 5, 0.0025, False, "BASELINE config 5: 262,144 envs x 500 assets, commission 0.0025, state-only"),
+    "c5_obs": (32768, 500, 50, 5, 0.0025, True, "wide universe with obs: 32,768 envs x 500 assets x window 50, commission 0.0025, obs materialised"),
     "c4_state": (131072, 100, 50, 5, 0.0, False, "config 4 shard, state-only step (no obs)"),
 }
 EPISODE_LEN = 1000
@@ -223,7 +224,6 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
     pool = [torch.randn(E, A, generator=gen, device=dev) for _ in range(n_pool)]   # "random actions": raw scores
     env.reset(obs=obs)
-    launches_per_step = 1                                     # fused step(+obs) kernel
     # steady state of a 1,000-step episode: the weight ring is full after W-1 steps (95 % of all steps), and only
     # then does the obs weight channel read the whole ring.  Pre-roll W state-only steps (untimed) to get there.
     preroll = W
@@ -235,8 +235,11 @@ def main():
     reducer = pdist.AsyncStatsReducer(dev) if world > 1 else None
     stats_in_sync = None
 
+    graph_launches_per_step = 0
     if args.graph:
+        c0 = _lib.load().pmrl_launch_count()
         static_actions, replay = env.graphed_step(obs=obs)
+        graph_launches_per_step = int(_lib.load().pmrl_launch_count() - c0) // 2     # one warm-up call + the captured call
 
         def one_step(i):
             static_actions.copy_(pool[i % n_pool])         # the policy would write its actions here
@@ -261,10 +264,14 @@ def main():
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    launches0 = _lib.load().pmrl_launch_count()               # kernels launched by libpmrl_b200, counted by the library itself
     ev0.record()
     for i in range(args.steps):
         one_step(args.warmup + i)
     ev1.record()
+    gpu_launches = int(_lib.load().pmrl_launch_count() - launches0)
+    if args.graph:
+        gpu_launches = graph_launches_per_step * args.steps      # replayed from the graph: counted at capture time
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
@@ -330,9 +337,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak,
                          "traffic": ncu_traffic_bytes(args.workload), "algorithmic_bytes_per_launch": bpa * E * A,
                          "bytes_per_asset_step": bpa, "peak_source": peak_src,
-                         "kernel": "k_env_step_obs_rt" if obs else "k_env_step"},
+                         "kernel": ("k_env_step_obs_rt" if gpu_launches == args.steps else "k_env_step + k_obs_build") if obs else "k_env_step"},
             "clocks": clocks,
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": gpu_launches,
             "stats": {k: stats[k] for k in ("n_envs", "mean_reward", "mean_value", "n_done")},
         }
         if reducer is not None:

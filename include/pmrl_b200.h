@@ -125,7 +125,9 @@ const char* pmrl_last_error(void);
 #define PMRL_TUNE_TILE_ROWS   1   /* asset-rows per obs tile of the fused kernel (power of two <= 32) */
 #define PMRL_TUNE_GROUP_ENVS  2   /* envs a CTA advances together (1..8) */
 #define PMRL_TUNE_CTAS_PER_SM 3   /* persistent CTAs per SM */
-#define PMRL_TUNE_FUSED       4   /* 1 (default): fused step+obs kernel; 0: k_env_step followed by k_obs_build */
+#define PMRL_TUNE_FUSED       4   /* 1 (default): fused step+obs kernel where a specialised one covers the shape, else k_env_step
+                                     followed by k_obs_build; 0: always the two kernels; 2: as 1 but the generic fused kernel
+                                     instead of the two-kernel fallback */
 #define PMRL_TUNE_FAST_FILL   5   /* 1 (default): specialised kernels (register-staged fill / TMA pipeline) when F == 5 && W <= 64 */
 #define PMRL_TUNE_TMA_PIPELINE 8  /* 1: warp-specialised TMA-load pipeline variant of the fused kernel (F == 5, W <= 64, A <= 512) */
 #define PMRL_TUNE_TMA_STAGES  9   /* staging buffers of that variant (2..6) */
@@ -133,6 +135,10 @@ const char* pmrl_last_error(void);
 #define PMRL_TUNE_TENSORMAP   12  /* 1: fused kernel variant whose feature windows arrive as tensor-map TMA boxes (env_step_tm.cu) */
 #define PMRL_TUNE_FAST_VARIANT 10 /* code-generation variant mask of the register-staged kernel (A/B measurement; see env_step_fast.cu) */
 int pmrl_set_tuning(int32_t key, int32_t value);
+
+/* Kernels this library has launched in this process so far (every entry point counts its own launches; bench.py reports
+ * the difference over its timed region as `gpu_launches`). */
+uint64_t pmrl_launch_count(void);
 
 /* Re-initialise the envs with mask[e] != 0 (mask == NULL → all): V ← initial_cash, ring ← 0 with
  * hist[e,0,0] = 1, idx ← 1, is_full ← 0, t ← 0, sharpe/ep_return cleared.  If obs_mode != NONE the

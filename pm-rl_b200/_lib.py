@@ -36,6 +36,7 @@ P = C.POINTER
 # symbol → (restype, argtypes); must list every function declared in include/pmrl_b200.h
 SIGNATURES = {
     "pmrl_abi_version": (C.c_int, []),
+    "pmrl_launch_count": (C.c_uint64, []),
     "pmrl_last_error": (C.c_char_p, []),
     "pmrl_set_tuning": (C.c_int, [i32, i32]),
     "pmrl_env_reset": (C.c_int, [P(PmrlEnvCfg), P(PmrlTables), P(PmrlEnvState), c_void_p, c_void_p, i32, c_void_p]),

@@ -5,7 +5,10 @@
 #include "pmrl_b200.h"
 #include "host_util.h"
 
+#include <atomic>
+
 static thread_local char g_err[256] = "";
+static std::atomic<unsigned long long> g_launches{0};
 
 int pmrl_fail(int code, const char* msg) {
     snprintf(g_err, sizeof(g_err), "pmrl_b200: %s", msg);
@@ -14,6 +17,7 @@ int pmrl_fail(int code, const char* msg) {
 
 int pmrl_check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e == cudaSuccess) return 0;
     snprintf(g_err, sizeof(g_err), "pmrl_b200: launch of %s failed: %s", what, cudaGetErrorString(e));
     return (int)e;
@@ -31,5 +35,6 @@ int pmrl_sm_count(void) {
     return cached[dev];
 }
 
+extern "C" uint64_t pmrl_launch_count(void) { return (uint64_t)g_launches.load(std::memory_order_relaxed); }
 extern "C" int pmrl_abi_version(void) { return PMRL_ABI_VERSION; }
 extern "C" const char* pmrl_last_error(void) { return g_err; }

@@ -105,10 +105,10 @@ def tuning():
 
 DEFAULT_TMA = 0
 DEFAULT_TM = 0
-# (fused, tile_rows, group_envs, tma, stages | fast): the fused step+obs kernel in several launch shapes (register-staged
+# (fused [2 = generic fused kernel instead of the two-kernel fallback], tile_rows, group_envs, tma, stages | fast): the fused step+obs kernel in several launch shapes (register-staged
 # fast fill, generic fill, warp-specialised TMA pipeline with 2..6 stages (tma=1), ring-through-TMA variant (tma=2), tensor-map TMA variant (tma=3))
 # and the two-kernel path
-VARIANTS = [(1, 0, 0, 0, 1), (1, 0, 3, 0, 1), (1, 8, 3, 0, 0), (1, 32, 1, 0, 0), (0, 0, 0, 0, 1),
+VARIANTS = [(1, 0, 0, 0, 1), (1, 0, 3, 0, 1), (2, 8, 3, 0, 0), (2, 32, 1, 0, 0), (0, 0, 0, 0, 1),
             (1, 0, 0, 1, 4), (1, 0, 2, 1, 2), (1, 0, 8, 1, 6), (1, 0, 0, 2, 1), (1, 0, 3, 2, 1), (1, 0, 5, 2, 1), (1, 0, 7, 2, 1),
             (1, 0, 0, 3, 1), (1, 0, 3, 3, 1)]
 
