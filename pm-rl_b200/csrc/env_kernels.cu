@@ -110,6 +110,69 @@ __global__ void __launch_bounds__(kObsThreads) k_obs_build(const StepParams p) {
 }
 
 
+// The same tile for the common shape (4 feature channels + weight slot, W <= 64, 32-asset tiles), without the
+// per-element index divisions of the generic fill: a warp owns an asset row of the feature window (lanes over window
+// rows, one float4 per row), and lanes run over assets for the weight channel (coalesced 128-byte ring rows).  All
+// loads of a thread are issued before the first shared store; the L2-resident table loads go first so that no
+// DRAM-latency ring load sits ahead of them in the L1 return queue.
+__global__ void __launch_bounds__(kObsThreads) k_obs_build_rows(const StepParams p) {
+    extern __shared__ __align__(128) float tile[];                  // [32][W][5]
+    const int A = p.A, W = p.W, T = p.T;
+    const int e = blockIdx.x / p.tiles_per_env;
+    const int ti = blockIdx.x - e * p.tiles_per_env;
+    if (p.mask && !p.mask[e]) return;
+    const int a0 = ti * 32;
+    const int na = min(32, A - a0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int idx = p.idx[e], full = p.is_full[e];
+    const int row0 = p.t0[e] + p.t[e];
+    const int shift = full ? 0 : (W - idx);                         // weight_buffer.py:38-42
+    const bool w0 = lane < W, w1 = lane + 32 < W;
+    const float4* __restrict__ tbl = reinterpret_cast<const float4*>(p.feat_am) + ((size_t)a0 * T + row0 + lane);
+    float4 fv[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int al = warp + 8 * i;
+        if (al < na) {
+            const float4* __restrict__ src = tbl + (size_t)al * T;
+            if (w0) fv[i][0] = ld_keep4(src, kPolicyEvictLast);
+            if (w1) fv[i][1] = ld_keep4(src + 32, kPolicyEvictLast);
+        }
+    }
+    const float* __restrict__ ring = p.hist + (size_t)e * W * A + a0 + lane;
+    float rv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int w = warp + 8 * j, slot = w - shift;
+        rv[j] = (w < W && slot >= 0 && lane < na) ? ld_once(ring + (size_t)slot * A, kPolicyEvictFirst) : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int al = warp + 8 * i;
+        if (al < na) {
+            float* d = tile + (al * W + lane) * 5;
+            if (w0) { const float4 v = fv[i][0]; d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+            if (w1) { const float4 v = fv[i][1]; d[160] = v.x; d[161] = v.y; d[162] = v.z; d[163] = v.w; }
+        }
+    }
+    if (lane < na) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int w = warp + 8 * j;
+            if (w < W) tile[(lane * W + w) * 5 + 4] = rv[j];
+        }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    float* __restrict__ dst = p.obs + ((size_t)e * A + a0) * W * 5;
+    const int n = na * W * 5;
+    if (((((uintptr_t)dst) | ((size_t)n * 4)) & 15) == 0) {
+        if (tid == 0) { bulk_store_s2g(dst, tile, (uint32_t)n * 4u, kPolicyEvictFirst); bulk_commit(); bulk_wait_read<0>(); }
+    } else {
+        for (int q = tid; q < n; q += kObsThreads) dst[q] = tile[q];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Mode O, fused: step + observation in one pass.
 //
@@ -317,8 +380,20 @@ static int check_obs_args(const StepParams& p, const float* obs, int obs_mode) {
     return 0;
 }
 
+// Launch-shape knobs (pmrl_set_tuning).
+static int g_tune_rows = 0, g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1, g_tune_fast = 1, g_tune_tma = 0, g_tune_stages = 0, g_tune_rt = 1, g_tune_tm = 0;
+
 static int launch_obs(StepParams& p, float* obs, int obs_mode, cudaStream_t s) {
     p.obs = obs; p.obs_mode = obs_mode;
+    if (obs_mode == PMRL_OBS_FULL && p.F == 5 && p.W <= 64 && p.t0 && g_tune_fast) {      // division-free tile kernel
+        if (p.E == 0) return 0;
+        p.tile_assets = 32;
+        p.tiles_per_env = (p.A + 31) / 32;
+        const long grid = (long)p.E * p.tiles_per_env;
+        if (grid > 2147483647L) return pmrl_fail(PMRL_E_SHAPE, "E * tiles_per_env exceeds the grid limit");
+        k_obs_build_rows<<<(unsigned)grid, kObsThreads, (size_t)32 * p.W * 5 * 4, s>>>(p);
+        return pmrl_check_launch("k_obs_build_rows");
+    }
     choose_obs_tile(p.A, p.W, p.F, kObsTileCapBytes, obs, p);
     if (p.E == 0) return 0;
     const size_t smem = (size_t)p.tile_assets * p.W * p.F * 4;
@@ -351,8 +426,6 @@ static int launch_step_npl(const StepParams& p, int npl, cudaStream_t s) {
     }
 }
 
-// Fused Mode-O launch: tile rows, group size and grid from the shape (tunable through pmrl_set_tuning).
-static int g_tune_rows = 0, g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1, g_tune_fast = 1, g_tune_tma = 0, g_tune_stages = 0, g_tune_rt = 1, g_tune_tm = 0;
 
 extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
     switch (key) {
