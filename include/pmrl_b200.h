@@ -228,6 +228,8 @@ int pmrl_pack_features(const float* series, const float* close, int32_t A, int32
 #define PMRL_IND_ADOSC  7   /* 3 / 10; needs the volume channel */
 #define PMRL_IND_CCI    8
 #define PMRL_IND_STOCH  9   /* 5 / 3 / 3: slowk, slowd */
+#define PMRL_IND_DX     10  /* Wilder directional movement index */
+#define PMRL_IND_ADX    11  /* Wilder-smoothed DX */
 int pmrl_indicator_layout(const int32_t* specs, int32_t n_specs, int32_t* n_out, int32_t* lookback);
 int pmrl_indicators(const float* series, int32_t A, int32_t C, int32_t L, const int32_t* specs, int32_t n_specs,
                     float* out, void* stream);

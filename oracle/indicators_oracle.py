@@ -116,3 +116,40 @@ def stoch(h, l, c):
         sd[t] = sk[t - 2:t + 1].mean()
     sk[:8] = np.nan
     return sk.astype(np.float32), sd.astype(np.float32)
+
+
+def _dm_tr(h, l, c):
+    h, l, c = (np.asarray(x, np.float64) for x in (h, l, c))
+    dp, dm = h[1:] - h[:-1], l[:-1] - l[1:]
+    plus = np.where((dp > 0) & (dp > dm), dp, 0.0); minus = np.where((dm > 0) & (dp < dm), dm, 0.0)
+    tr = np.maximum(h[1:] - l[1:], np.maximum(np.abs(h[1:] - c[:-1]), np.abs(l[1:] - c[:-1])))
+    return plus, minus, tr                                   # element q belongs to bar q + 1
+
+
+def dx(h, l, c, n, _with_flags=False):
+    """ta_DX.c: bars 1..n-1 accumulate, from bar n Wilder smoothing; a zero denominator repeats the previous value."""
+    plus, minus, tr = _dm_tr(h, l, c); L = len(tr) + 1
+    out = np.full(L, np.nan); have = np.zeros(L, bool)
+    p, m, t_ = plus[:n - 1].sum(), minus[:n - 1].sum(), tr[:n - 1].sum()
+    prev = 0.0
+    for t in range(n, L):
+        p = p - p / n + plus[t - 1]; m = m - m / n + minus[t - 1]; t_ = t_ - t_ / n + tr[t - 1]
+        if t_ != 0:
+            pdi, mdi = 100 * (p / t_), 100 * (m / t_)
+            if pdi + mdi != 0:
+                prev = 100 * (abs(mdi - pdi) / (pdi + mdi)); have[t] = True
+        out[t] = prev
+    return (out, have) if _with_flags else out.astype(np.float32)
+
+
+def adx(h, l, c, n):
+    """ta_ADX.c: mean of the first n DX values at index 2n-1, then (ADX*(n-1) + DX)/n; undefined DX bars add nothing."""
+    d, have = dx(h, l, c, n, _with_flags=True); L = len(d)
+    out = np.full(L, np.nan)
+    a = sum(d[t] for t in range(n, 2 * n) if have[t]) / n
+    out[2 * n - 1] = a
+    for t in range(2 * n, L):
+        if have[t]:
+            a = (a * (n - 1) + d[t]) / n
+        out[t] = a
+    return out.astype(np.float32)

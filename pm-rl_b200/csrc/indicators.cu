@@ -1,7 +1,7 @@
 // indicators.cu — technical-indicator windows of the feature path (data/instrument.py:207-232 runs TA-Lib's abstract
 // functions on the float64 OHLCV and appends the float32 outputs; the indicator set is config/base.py:30-44).
 // TA-Lib itself is not vendored with the reference (no version pin) → the formulas below restate TA-Lib's published
-// algorithms (ta_SMA.c, ta_EMA.c, ta_RSI.c, ta_ATR.c, ta_BBANDS.c, ta_MACD.c; default unstable period 0) in double
+// algorithms (ta_SMA.c, ta_EMA.c, ta_RSI.c, ta_ATR.c, ta_BBANDS.c, ta_MACD.c, ta_DX.c, ta_ADX.c …; default unstable period 0) in double
 // precision like TA-Lib computes them; parity against TA-Lib is UNPINNED.
 //
 // One thread per (asset, indicator): every indicator is a sequential scan over the series (one-time preprocessing).
@@ -162,6 +162,36 @@ __global__ void k_indicators(const float* __restrict__ series, int A, int C, int
             o0[t] = (float)slowk; o1[t] = (float)((sk[0] + sk[1] + sk[2]) / 3.0);
         }
     } break;
+    case PMRL_IND_DX:
+    case PMRL_IND_ADX: {                                                                      // Wilder directional movement (ta_DX.c / ta_ADX.c)
+        // bars 1..n-1 accumulate +DM, -DM and TR; from bar n on each is Wilder-smoothed (x ← x − x/n + today) and
+        // DX = 100·|+DI − −DI| / (+DI + −DI) (first value at index n, a zero denominator repeats the previous DX);
+        // ADX = mean of the first n DX values (index 2n−1), then (ADX·(n−1) + DX) / n.
+        const bool adx = sp.kind[s] == PMRL_IND_ADX;
+        double pdm = 0.0, mdm = 0.0, tr = 0.0, dx = 0.0, sum_dx = 0.0, ax = 0.0;
+        if (L > 0) o0[0] = nan;
+        for (int t = 1; t < L; ++t) {
+            const double h = hi[t], l = lo[t], ph = hi[t - 1], pl = lo[t - 1], pc = cl[t - 1];
+            const double dp = h - ph, dm = pl - l;
+            const double plus = (dp > 0.0 && dp > dm) ? dp : 0.0, minus = (dm > 0.0 && dp < dm) ? dm : 0.0;
+            const double trt = fmax(h - l, fmax(fabs(h - pc), fabs(l - pc)));
+            if (t < n) { pdm += plus; mdm += minus; tr += trt; o0[t] = nan; continue; }
+            pdm = pdm - pdm / n + plus; mdm = mdm - mdm / n + minus; tr = tr - tr / n + trt;
+            bool have = false;
+            if (tr != 0.0) {
+                const double pdi = 100.0 * (pdm / tr), mdi = 100.0 * (mdm / tr), sm = pdi + mdi;
+                if (sm != 0.0) { dx = 100.0 * (fabs(mdi - pdi) / sm); have = true; }
+            }
+            if (!adx) { o0[t] = (float)dx; continue; }          // DX: an undefined bar repeats the previous value (0 at the start)
+            if (t < 2 * n) {                                     // the first n DX values seed the ADX (undefined bars add nothing)
+                if (have) sum_dx += dx;
+                if (t == 2 * n - 1) { ax = sum_dx / n; o0[t] = (float)ax; } else o0[t] = nan;
+            } else {
+                if (have) ax = (ax * (n - 1) + dx) / n;
+                o0[t] = (float)ax;
+            }
+        }
+    } break;
     default: break;
     }
 }
@@ -180,6 +210,8 @@ static int spec_lookback(int kind, int n) {
         case PMRL_IND_ADOSC: return 9;
         case PMRL_IND_CCI: return n - 1;
         case PMRL_IND_STOCH: return 8;
+        case PMRL_IND_DX: return n;
+        case PMRL_IND_ADX: return 2 * n - 1;
         default: return -1;
     }
 }

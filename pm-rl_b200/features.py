@@ -153,11 +153,11 @@ class FixedFracDiff:
 # ---------------------------------------------------------------------------------------------------------------
 # Indicator windows (data/instrument.py:207-232; config/base.py:30-44)
 # ---------------------------------------------------------------------------------------------------------------
-INDICATOR_KINDS = {"sma": 0, "ema": 1, "rsi": 2, "atr": 3, "bbands": 4, "macd": 5, "obv": 6, "adosc": 7, "cci": 8, "stoch": 9}
+INDICATOR_KINDS = {"sma": 0, "ema": 1, "rsi": 2, "atr": 3, "bbands": 4, "macd": 5, "obv": 6, "adosc": 7, "cci": 8, "stoch": 9, "dx": 10, "adx": 11}
 _IND_OUTPUTS = {"sma": ["sma"], "ema": ["ema"], "rsi": ["rsi"], "atr": ["atr"],
                 "bbands": ["upperband", "middleband", "lowerband"], "macd": ["macd", "macdsignal", "macdhist"],
-                "obv": ["obv"], "adosc": ["adosc"], "cci": ["cci"], "stoch": ["slowk", "slowd"]}
-_IND_DEFAULT_PERIOD = {"sma": 30, "ema": 30, "rsi": 14, "atr": 14, "bbands": 5, "macd": 0, "obv": 0, "adosc": 0, "cci": 14, "stoch": 0}
+                "obv": ["obv"], "adosc": ["adosc"], "cci": ["cci"], "stoch": ["slowk", "slowd"], "dx": ["dx"], "adx": ["adx"]}
+_IND_DEFAULT_PERIOD = {"sma": 30, "ema": 30, "rsi": 14, "atr": 14, "bbands": 5, "macd": 0, "obv": 0, "adosc": 0, "cci": 14, "stoch": 0, "dx": 14, "adx": 14}
 
 
 def add_indicators(ohlcv, indicators):

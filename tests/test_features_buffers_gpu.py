@@ -292,7 +292,25 @@ def test_indicator_windows_vs_oracle():
     # analytic checks: cash (asset 0, constant price): EMA = price, bands collapse, RSI = 0 (no gains), ATR = 0
     np.testing.assert_allclose(got[0, 0], 1.0); np.testing.assert_allclose(got[0, 2], got[0, 4]); assert (got[0, 9] == 0).all()
     with pytest.raises(NotImplementedError):
-        features.add_indicators(tbl, {"adx": {"timeperiod": 30}})
+        features.add_indicators(tbl, {"sar": {}})
+
+
+def test_directional_movement_indicators_vs_oracle():
+    """adx / dx of the reference's commented default set (config/base.py:38-39)."""
+    from oracle import indicators_oracle as io
+    from pmrl_b200 import features, synth
+    T, A = 300, 6
+    tbl = synth.gbm_ohlc(T, A, seed=21)
+    names, out, lb = features.add_indicators(tbl, [("adx", {"timeperiod": 30}), ("dx", {"timeperiod": 30}), ("adx", {"timeperiod": 5})])
+    assert lb == 59 and out.shape == (A, 3, T - lb) and names == ["adx_30", "dx_30", "adx_5"]
+    got = out.cpu().numpy()
+    o, h, l, c = (tbl[:, :, i].numpy().T for i in range(4))
+    for a in range(A):
+        want = [io.adx(h[a], l[a], c[a], 30), io.dx(h[a], l[a], c[a], 30), io.adx(h[a], l[a], c[a], 5)]
+        for j, w in enumerate(want):
+            np.testing.assert_allclose(got[a, j], w[lb:], rtol=2e-6, atol=1e-5, err_msg=f"asset {a} {names[j]}")
+    assert np.isfinite(got).all() and (got >= 0).all() and (got <= 100.0 + 1e-4).all()
+    assert (got[0] == 0).all()                                   # cash: no range, no movement → DX = ADX = 0
 
 
 def test_volume_and_oscillator_indicators_vs_oracle():
