@@ -181,6 +181,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=0,
                     help="env slices of the host-buffer step: >0 geometric x2.5, <0 equal, 0 library default (5 geometric)")
+    ap.add_argument("--stats-every", type=int, default=1,
+                    help="multi-GPU: all-reduce the stats vector over NCCL every K steps (SURVEY 8e: K = 1); 0 = only at the end")
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (launch-bound small batches)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VAL",
                     help="kernel launch-shape override: rows|group|ctas|fused|fast = int (pmrl_set_tuning)")
@@ -232,7 +234,7 @@ def main():
 
     # multi-GPU: the 10-double stats vector is all-reduced over NCCL EVERY step (SURVEY.md §8(e), K = 1), issued
     # asynchronously behind a snapshot so the next step's kernel is not ordered after the collective
-    reducer = pdist.AsyncStatsReducer(dev) if world > 1 else None
+    reducer = pdist.AsyncStatsReducer(dev) if (world > 1 and args.stats_every > 0) else None
     stats_in_sync = None
 
     graph_launches_per_step = 0
@@ -247,7 +249,7 @@ def main():
     else:
         def one_step(i):
             env.step(pool[i % n_pool], obs=obs)
-            if reducer is not None:
+            if reducer is not None and i % args.stats_every == 0:
                 reducer.launch(env._stats)
 
     def barrier():
@@ -282,7 +284,7 @@ def main():
     if reducer is not None:                                   # the last step's reduced vector must equal a fresh reduce
         last = reducer.result()
         fresh = pdist.all_reduce_stats(env._stats.clone())
-        stats_in_sync = bool(torch.allclose(last, fresh, rtol=1e-12, atol=0.0))
+        stats_in_sync = bool(torch.allclose(last, fresh, rtol=1e-12, atol=0.0)) if args.stats_every == 1 else None
     stats = env.stats(all_reduce=world > 1)                   # NCCL all-reduce of the 10-double stats vector
 
     # ---- end to end through the public API with host buffers (H2D actions, D2H reward/done every step) ----
@@ -343,7 +345,7 @@ def main():
             "stats": {k: stats[k] for k in ("n_envs", "mean_reward", "mean_value", "n_done")},
         }
         if reducer is not None:
-            line["stats_allreduce"] = {"every_steps": 1, "launches": reducer.launches, "last_equals_fresh_reduce": stats_in_sync}
+            line["stats_allreduce"] = {"every_steps": args.stats_every, "launches": reducer.launches, "last_equals_fresh_reduce": stats_in_sync}
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <type_traits>
+#include <atomic>
 #include "pmrl_b200.h"
 #include "pmrl_device.cuh"
 #include "env_step.cuh"
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
     __shared__ double s_stats[kRtWarps * PMRL_STATS_LEN];
     __shared__ RtEnv s_env[kRtGroup];
     __shared__ __align__(8) uint64_t s_rbar[2];
+    __shared__ int s_next;
     const int W = WT ? WT : p.W;
     const int A = p.A, T = p.T, G = p.group_envs;
     const int WA = W * A;
@@ -58,9 +60,15 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
 
     int buf = 0;
     int ebase = 0;                                                   // envs streamed by this CTA so far (ring buffer / phase index)
-    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    // Groups are handed out dynamically: the first one is the CTA's own index, every further one a ticket from a global
+    // counter.  A static stride leaves 16,384 groups on 296 CTAs as 55 or 56 rounds (a 1.8 % tail), and a CTA that starts
+    // late — e.g. behind a concurrent NCCL kernel holding its SM's shared memory — would finish a whole round late.
+    int grp = blockIdx.x;
+    while (grp < n_groups) {
         const int e0 = grp * G;
         const int ne = min(G, p.E - e0);
+        unsigned int ticket = 0;
+        if (tid == 0) ticket = atomicAdd(p.ticket, 1u);               // consumed after phase 1: its latency hides under the step
         // ---------------- phase 1: one warp per env ----------------
         if (warp < ne) {
             const int e = e0 + warp;
@@ -81,7 +89,9 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
                 s_env[warp] = ge;
             }
         }
+        if (tid == 0) s_next = (int)(gridDim.x + ticket);
         __syncthreads();
+        const int next_grp = s_next;                                  // (rewritten only after the tile loop's barriers)
         // ---------------- phase 2 ----------------
         const int R = ne * A;
         const int ntiles = (R + 31) >> 5, nfull = R >> 5;
@@ -169,14 +179,39 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
             buf ^= 1;
         }
         ebase += ne;
+        grp = next_grp;
     }
-    if (tid == 0) bulk_wait_read<0>();
+    if (tid == 0) {
+        bulk_wait_read<0>();
+        // the last CTA out re-arms the counters for the next launch that uses this slot
+        __threadfence();
+        if (atomicAdd(p.ticket + 1, 1u) == gridDim.x - 1) { p.ticket[0] = 0u; p.ticket[1] = 0u; __threadfence(); }
+    }
     if (p.stats) stats_flush_block(p.stats, s_stats, kRtWarps);
 }
 
 }  // namespace pmrl
 
 using namespace pmrl;
+
+// Ticket counters of the dynamic group hand-out: 64 {ticket, finished} pairs in device memory, used round-robin by
+// consecutive launches (so launches in flight on different streams do not share one) and reset by the last CTA of
+// the launch that used them.
+constexpr int kTicketSlots = 64;
+__device__ unsigned int g_rt_tickets[kTicketSlots][2];
+
+static unsigned int* next_ticket_slot() {
+    static unsigned int* base[64] = {nullptr};
+    static std::atomic<unsigned int> turn{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!base[dev]) {
+        void* ptr = nullptr;
+        if (cudaGetSymbolAddress(&ptr, g_rt_tickets) != cudaSuccess) return nullptr;
+        base[dev] = (unsigned int*)ptr;
+    }
+    return base[dev] + 2 * (turn.fetch_add(1, std::memory_order_relaxed) % kTicketSlots);
+}
 
 template <int NPL, bool HASC, int WT>
 static int launch_rt_t(StepParams& p, size_t smem, int grid, cudaStream_t s) {
@@ -228,6 +263,8 @@ int pmrl_launch_step_obs_rt(StepParams& p, int npl, int group, int ctas_per_sm, 
     if (smem > (size_t)(226 * 1024) / per_sm - 1024) return -100;
     const int n_groups = (p.E + G - 1) / G;
     const int grid = n_groups < slots ? n_groups : slots;
+    p.ticket = next_ticket_slot();
+    if (!p.ticket) return -100;
     const bool hasc = p.commission > 0.0f;
 #define RT_CASE(N) return hasc ? launch_rt_w<N, true>(p, smem, grid, s) : launch_rt_w<N, false>(p, smem, grid, s)
     switch (npl) {

@@ -48,17 +48,20 @@ def all_reduce_stats(stats: torch.Tensor) -> torch.Tensor:
 
 
 class AsyncStatsReducer:
-    """All-reduce of the statistics vector every step, off the step's critical path (one SUM over 8
-    doubles + one MAX over 2, K = 1 for config 4).  launch() snapshots the running vector into private buffers and
-    starts both collectives asynchronously (NCCL runs them on its own stream behind the snapshot); the next step's
-    kernel is not ordered after them.  result() waits and returns the reduced 10-vector of the last launch."""
+    """All-reduce of the statistics vector every step, off the step's critical path (SUM over 8
+    doubles, MAX over 2, K = 1 for config 4).  launch() snapshots the running vector into a private buffer (one small
+    copy on the caller's stream) and starts ONE asynchronous collective — an all-gather of the 10 doubles, so that the
+    SUM and the MAX part travel together; NCCL runs it on its own stream behind the snapshot and the next step's kernel
+    is not ordered after it.  result() waits and folds the gathered [world, 10] block (sum over ranks / max over ranks).
+    Measured on 2 x B200 at config 4: two all-reduces per step cost 1.4 % of the step, see DESIGN.md §6."""
 
     def __init__(self, device, dtype=torch.float64):
-        self.sums = torch.zeros(N_SUM_STATS, dtype=dtype, device=device)
-        self.maxs = torch.zeros(2, dtype=dtype, device=device)
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.world = dist.get_world_size() if self.active else 1
+        self.snap = torch.zeros(N_SUM_STATS + 2, dtype=dtype, device=device)
+        self.gathered = torch.zeros(self.world * (N_SUM_STATS + 2), dtype=dtype, device=device)
         self.pending = []
         self.launches = 0
-        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
     def _drain(self):
         for w in self.pending:
@@ -67,13 +70,14 @@ class AsyncStatsReducer:
 
     def launch(self, stats: torch.Tensor):
         self._drain()
-        self.sums.copy_(stats[:N_SUM_STATS])
-        self.maxs.copy_(stats[N_SUM_STATS:])
+        self.snap.copy_(stats)
         if self.active:
-            self.pending = [dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, async_op=True),
-                            dist.all_reduce(self.maxs, op=dist.ReduceOp.MAX, async_op=True)]
+            self.pending = [dist.all_gather_into_tensor(self.gathered, self.snap, async_op=True)]
         self.launches += 1
 
     def result(self) -> torch.Tensor:
         self._drain()
-        return torch.cat([self.sums, self.maxs])
+        if not self.active:
+            return self.snap.clone()
+        g = self.gathered.view(self.world, N_SUM_STATS + 2)
+        return torch.cat([g[:, :N_SUM_STATS].sum(dim=0), g[:, N_SUM_STATS:].max(dim=0).values])
