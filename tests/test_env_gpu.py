@@ -524,3 +524,23 @@ def test_shared_divisor_quotients_equal_ieee_division_bit_for_bit():
     # out-of-range operands are skipped, not mis-divided
     bad, tested = run(torch.full((64,), 1e-30, device="cuda"), torch.ones(2, device="cuda"))
     assert (bad, tested) == (0, 0)
+
+
+def test_launch_counter_tells_the_fused_path_from_the_two_kernel_path():
+    """pmrl_launch_count (bench.py's gpu_launches): one kernel per step where a specialised fused kernel covers the shape,
+    two (step + obs tile kernel) elsewhere, one for a state-only step."""
+    from pmrl_b200 import _lib
+    lib = _lib.load()
+
+    def launches(A, obs):
+        gpu, _ = make_pair(16, A, 8, 5, episode_len=20)
+        gpu.reset(obs=obs)
+        act = torch.randn(16, A, device="cuda")
+        c0 = lib.pmrl_launch_count()
+        gpu.step(act, obs=obs)
+        return lib.pmrl_launch_count() - c0
+
+    assert launches(40, True) == 1        # RT kernel
+    assert launches(12, True) == 1        # register-ring kernel (A < 32)
+    assert launches(200, True) == 2       # wide universe: k_env_step + k_obs_build_rows
+    assert launches(200, False) == 1

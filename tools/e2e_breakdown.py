@@ -70,7 +70,10 @@ def main():
         torch.cuda.synchronize()
     wall(lambda i: zero_copy(i, False), "zero-copy actions (kernel reads pinned host memory) + D2H copies")
     wall(lambda i: zero_copy(i, True), "zero-copy actions + kernel writes reward/done to pinned host memory")
-    for c in (-1, 3, 6):
+    wall(lambda i: zero_copy(i, False), "(repeat) zero-copy actions + D2H copies")
+    wall(lambda i: zero_copy(i, True), "(repeat) zero-copy actions + host-mapped reward/done")
+    wall(lambda i: env.step_host(h_act[i % 2], h_r, h_d, chunks=0), "pmrl_env_step_host slices=0 (zero-copy default)")
+    for c in (-1, 3, 6, 0):
         wall(lambda i: env.step_host(h_act[i % 2], h_r, h_d, chunks=c), f"pmrl_env_step_host slices={c}")
 
 
