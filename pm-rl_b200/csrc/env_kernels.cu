@@ -510,6 +510,7 @@ static int launch_fused(StepParams& p, float* obs, int npl, cudaStream_t s) {
 
 extern "C" int pmrl_env_reset(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
                               const uint8_t* mask, float* obs, int32_t obs_mode, void* stream) {
+    if (cfg && cfg->E == 0) return 0;                  // empty batch: nothing to do (state pointers may be NULL)
     StepParams p;
     if (int rc = fill_params(cfg, tbl, st, p)) return rc;
     if (int rc = check_obs_args(p, obs, obs_mode)) return rc;
@@ -569,6 +570,7 @@ extern "C" int pmrl_selftest_division(const float* num, const float* den, int64_
 
 extern "C" int pmrl_obs_build(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
                               float* obs, int32_t obs_mode, void* stream) {
+    if (cfg && cfg->E == 0) return 0;                  // empty batch: nothing to do (state pointers may be NULL)
     StepParams p;
     if (int rc = fill_params(cfg, tbl, st, p)) return rc;
     if (obs_mode == PMRL_OBS_NONE) return pmrl_fail(PMRL_E_ARG, "obs_mode NONE makes no obs");
@@ -581,6 +583,7 @@ extern "C" int pmrl_env_step(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const
                              const float* actions, const float* y_ext,
                              float* reward, uint8_t* done, float* obs, int32_t obs_mode,
                              double* stats, void* stream) {
+    if (cfg && cfg->E == 0) return 0;                  // empty batch: nothing to do (state pointers may be NULL)
     StepParams p;
     if (int rc = fill_params(cfg, tbl, st, p)) return rc;
     if (!actions || !reward || !done) return pmrl_fail(PMRL_E_ARG, "actions/reward/done is NULL");

@@ -88,6 +88,7 @@ extern "C" int pmrl_env_step_host(const PmrlEnvCfg* cfg, const PmrlTables* tbl, 
                                   const float* actions_host, float* actions_stage,
                                   float* reward, uint8_t* done, float* reward_host, uint8_t* done_host,
                                   float* obs, int32_t obs_mode, double* stats, int32_t slices, void* stream) {
+    if (cfg && cfg->E == 0) return 0;
     if (!cfg || !tbl || !st || !actions_host || !actions_stage || !reward || !done || !reward_host || !done_host)
         return pmrl_fail(PMRL_E_ARG, "env_step_host: null argument");
     if (cfg->E <= 0 || cfg->A <= 0 || cfg->W <= 0 || cfg->F <= 0) return pmrl_fail(PMRL_E_SHAPE, "env_step_host: bad sizes");
