@@ -34,7 +34,7 @@
  *
  * Device data layout (all fp32 unless noted; E = envs on this GPU, A = assets incl.
  * cash at index 0, W = window, F = obs channels incl. the weight slot which is LAST):
- *   close_tm [T, A]        time-major close plane; y_t[a] = close_tm[t,a] / close_tm[t-1,a]
+ *   y_tm     [T, A]        time-major price relatives y_t[a] = close[t,a] / close[t-1,a] (pmrl_price_relatives)
  *   feat_am  [A, T, F-1]   asset-major feature table (OHLC, or FFD'ed + scaled series)
  *   value    [E]           portfolio value V
  *   hist     [E, W, A]     ring of post-drift weights (reference ActionBuffer.buffer per env)
@@ -76,7 +76,7 @@ extern "C" {
 
 typedef struct PmrlEnvCfg {
     int32_t E, A, W, F;        /* envs on this device, assets, window, obs channels (weight slot = F-1) */
-    int32_t T;                 /* rows of close_tm / feat_am */
+    int32_t T;                 /* rows of y_tm / feat_am */
     int32_t episode_len;       /* L_ep: done when local step == L_ep; <= 0 → episodes never end */
     int32_t reward_mode;       /* PMRL_REWARD_* */
     int32_t mu_max_iter;       /* cap on the commission fixed-point iterations (trading_env.py:70) */
@@ -148,7 +148,7 @@ int pmrl_env_reset(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvSt
 
 /* One lockstep transition of all E envs.
  *   actions [E, A]  raw scores or weights (normalised in-kernel like trading_env.py:58-60)
- *   y_ext   [E, A]  externally supplied price relatives, or NULL → computed from tbl->close_tm
+ *   y_ext   [E, A]  externally supplied price relatives, or NULL → row t0+k+W-1 of tbl->y_tm
  *   reward  [E]     out;  done [E] u8 out (local step reached episode_len)
  *   obs             out [E,A,W,F] (FULL), in/out (WEIGHTS), or NULL (NONE)
  *   stats           double[PMRL_STATS_LEN] device vector or NULL
