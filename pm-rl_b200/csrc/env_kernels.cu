@@ -480,6 +480,7 @@ static int launch_fused(StepParams& p, float* obs, int npl, cudaStream_t s) {
         if (rc != -100) return rc;
     }
     if (g_tune_fast && g_tune_rt) {                   // ring rows through one TMA bulk load per env (env_step_rt.cu)
+        p.tma_stages = (g_tune_rt == 2) ? 0 : 1;      // RT reuses this field: 1 = prefetch the next group's phase-1 inputs into L2
         const int rc = pmrl_launch_step_obs_rt(p, npl, g_tune_group, g_tune_ctas_per_sm, s);
         if (rc != -100) return rc;
     }

@@ -92,6 +92,16 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
         if (tid == 0) s_next = (int)(gridDim.x + ticket);
         __syncthreads();
         const int next_grp = s_next;                                  // (rewritten only after the tile loop's barriers)
+        // pull what phase 1 of the next group will read from DRAM (raw actions, scalar state) into L2 while this group
+        // streams: its dependent chain scalars → addresses → vectors then runs on L2 hits
+        if (p.tma_stages && next_grp < n_groups) {
+            const int ne_next = min(G, p.E - next_grp * G);
+            const size_t a_first = (size_t)next_grp * G * A;
+            const int a_lines = (ne_next * A + 31) >> 5;              // 128-byte lines of the group's action rows
+            for (int q = tid; q < a_lines; q += kRtThreads) prefetch_l2(p.actions + a_first + (size_t)q * 32);
+            if (tid == 32) { prefetch_l2(p.value + next_grp * G); prefetch_l2(p.idx + next_grp * G); prefetch_l2(p.t + next_grp * G); }
+            if (tid == 64) { prefetch_l2(p.t0 + next_grp * G); prefetch_l2(p.is_full + next_grp * G); if (p.ep_return) prefetch_l2(p.ep_return + next_grp * G); }
+        }
         // ---------------- phase 2 ----------------
         const int R = ne * A;
         const int ntiles = (R + 31) >> 5, nfull = R >> 5;
