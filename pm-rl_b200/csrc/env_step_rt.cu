@@ -4,7 +4,7 @@
 // Same structure as env_step_fast.cu (persistent CTAs, groups of G <= 8 envs, 32-asset-row tiles, register-staged
 // table loads, one TMA bulk store per tile) with these differences:
 //   * ring rows never travel through registers or the L1 load queue: thread 0 issues cp.async.bulk global→shared for
-//     the whole ring of env el (double-buffered: envs el and el+1 resident), completion on an mbarrier; the weight
+//     the whole ring of env el (2-4 rings resident: envs el .. el+NB-1), completion on an mbarrier; the weight
 //     channel of a tile is then filled from shared memory (lanes over assets: conflict-free).  The L1 queue only
 //     carries the L2-hit table loads, so no DRAM-latency load can sit in front of them, and DRAM sees one
 //     page-friendly 20 KB read per env instead of 200 scattered 128-byte reads;
@@ -25,7 +25,8 @@ namespace pmrl {
 
 constexpr int kRtThreads = 256;
 constexpr int kRtWarps = kRtThreads / 32;
-constexpr int kRtGroup = kRtWarps;
+constexpr int kRtGroup = kRtWarps;                 // envs per group, one per warp (A > 64)
+constexpr int kRtGroupNarrow = 2 * kRtWarps;       // A <= 64: two envs per warp
 
 struct RtEnv { int row0, shift, fresh_slot, pad; };
 struct RtFeat { float4 fv[4][2]; };
@@ -34,8 +35,8 @@ template <int NPL, bool HASC, int WT>
 __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_stats[kRtWarps * PMRL_STATS_LEN];
-    __shared__ RtEnv s_env[kRtGroup];
-    __shared__ __align__(8) uint64_t s_rbar[2];
+    __shared__ RtEnv s_env[kRtGroupNarrow];
+    __shared__ __align__(8) uint64_t s_rbar[4];
     __shared__ int s_next;
     const int W = WT ? WT : p.W;
     const int A = p.A, T = p.T, G = p.group_envs;
@@ -44,12 +45,13 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
     float* const tile0 = reinterpret_cast<float*>(smem_raw);
     float* const tile1 = tile0 + tile_floats;
     float* const s_ring = tile1 + tile_floats;                       // [2][W*A] rings of two consecutive envs
-    float* const s_wnew = s_ring + 2 * WA;                           // [G*A]    w' per asset-row of the group
+    const int NB = p.ring_bufs;                                      // rings resident at once (2 at A = 100, up to 4 for narrow envs)
+    float* const s_wnew = s_ring + NB * WA;                          // [G*A]    w' per asset-row of the group
     int* const s_ea = reinterpret_cast<int*>(s_wnew + G * A);        // [G*A]    (env-in-group << 16) | asset
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_groups = (p.E + G - 1) / G;
     const size_t row_floats = (size_t)W * 5;
-    if (tid == 0) { mbar_init(&s_rbar[0], 1); mbar_init(&s_rbar[1], 1); mbar_fence_init(); }
+    if (tid == 0) { for (int b = 0; b < 4; ++b) mbar_init(&s_rbar[b], 1); mbar_fence_init(); }
     if (p.stats) stats_init_block(s_stats, kRtWarps); else __syncthreads();
 
     const int fbase = (warp * W + lane) * 5, fstep = 8 * W * 5;
@@ -69,25 +71,40 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
         const int ne = min(G, p.E - e0);
         unsigned int ticket = 0;
         if (tid == 0) ticket = atomicAdd(p.ticket, 1u);               // consumed after phase 1: its latency hides under the step
-        // ---------------- phase 1: one warp per env ----------------
-        if (warp < ne) {
-            const int e = e0 + warp;
-            EnvVectors<NPL, HASC> ev;
-            StepOut so;
-            env_step_warp<NPL, HASC>(p, e, lane, ev, so, s_stats + warp * PMRL_STATS_LEN);
+        // ---------------- phase 1: one warp per env (two per warp for narrow envs: groups of up to 16) ----------------
+        auto publish = [&](int el, const EnvVectors<NPL, HASC>& ev, const StepOut& so) {
 #pragma unroll
             for (int j = 0; j < NPL; ++j) {
                 const int a = lane + 32 * j;
-                if (a < A) { s_wnew[warp * A + a] = ev.a[j]; s_ea[warp * A + a] = (warp << 16) | a; }
+                if (a < A) { s_wnew[el * A + a] = ev.a[j]; s_ea[el * A + a] = (el << 16) | a; }
             }
             if (lane == 0) {
                 RtEnv ge;
-                ge.row0 = p.t0[e] + so.k;
+                ge.row0 = p.t0[e0 + el] + so.k;
                 ge.shift = so.is_full ? 0 : (W - so.idx_new);          // weight_buffer.py:38-42
                 ge.fresh_slot = so.did_reset ? 0 : so.slot_written;     // the row written by this launch comes from smem
                 ge.pad = 0;
-                s_env[warp] = ge;
+                s_env[el] = ge;
             }
+        };
+        if constexpr (NPL <= 2) {
+            // A <= 64: an env is only 50-odd rows of streaming, so the step latency weighs twice as much per byte as at
+            // A = 100.  Each warp advances two envs with their loads issued together (scalars, then vectors, then the math).
+            const int el0 = warp, el1 = warp + kRtWarps;
+            EnvScalars sc0, sc1;
+            EnvVectors<NPL, HASC> ev0, ev1;
+            StepOut so;
+            if (el0 < ne) env_load_scalars(p, e0 + el0, sc0);
+            if (el1 < ne) env_load_scalars(p, e0 + el1, sc1);
+            if (el0 < ne) env_load_vectors<NPL, HASC>(p, e0 + el0, lane, sc0, ev0);
+            if (el1 < ne) env_load_vectors<NPL, HASC>(p, e0 + el1, lane, sc1, ev1);
+            if (el0 < ne) { env_compute_store<NPL, HASC>(p, e0 + el0, lane, sc0, ev0, so, s_stats + warp * PMRL_STATS_LEN); publish(el0, ev0, so); }
+            if (el1 < ne) { env_compute_store<NPL, HASC>(p, e0 + el1, lane, sc1, ev1, so, s_stats + warp * PMRL_STATS_LEN); publish(el1, ev1, so); }
+        } else if (warp < ne) {
+            EnvVectors<NPL, HASC> ev;
+            StepOut so;
+            env_step_warp<NPL, HASC>(p, e0 + warp, lane, ev, so, s_stats + warp * PMRL_STATS_LEN);
+            publish(warp, ev, so);
         }
         if (tid == 0) s_next = (int)(gridDim.x + ticket);
         __syncthreads();
@@ -111,11 +128,12 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
         auto issue_rings = [&](int upto) {                            // thread 0 only
             for (; issued < upto; ++issued) {
                 const int n = ebase + issued;
-                mbar_arrive_expect_tx(&s_rbar[n & 1], (uint32_t)WA * 4u);
-                bulk_load_g2s(s_ring + (n & 1) * WA, hist_g + (size_t)issued * WA, (uint32_t)WA * 4u, &s_rbar[n & 1], kPolicyEvictFirst);
+                const int b = n % NB;
+                mbar_arrive_expect_tx(&s_rbar[b], (uint32_t)WA * 4u);
+                bulk_load_g2s(s_ring + b * WA, hist_g + (size_t)issued * WA, (uint32_t)WA * 4u, &s_rbar[b], kPolicyEvictFirst);
             }
         };
-        if (tid == 0) issue_rings(min(ne, 2));
+        if (tid == 0) issue_rings(min(ne, NB));
         int wel = lane / A, wa = lane - wel * A;                      // (env-in-group, asset) of this lane's weight row
 
         auto load_feat = [&](RtFeat& fr, int r0, auto partial) {
@@ -144,9 +162,10 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
             }
             if (!PARTIAL || lane < nr) {                              // weight channel straight from the staged ring
                 const int n = ebase + wel;
-                mbar_wait(&s_rbar[n & 1], (uint32_t)((n >> 1) & 1));
+                const int b = n % NB;
+                mbar_wait(&s_rbar[b], (uint32_t)((n / NB) & 1));
                 const RtEnv ge = s_env[wel];
-                const float* __restrict__ rs = s_ring + (n & 1) * WA + wa;
+                const float* __restrict__ rs = s_ring + b * WA + wa;
                 const float fresh = s_wnew[r0 + lane];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -185,7 +204,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
             }
             // envs below (r0+32)/A are complete (every thread passed the barrier after its last read of their ring):
             // their buffers can take the rings of the envs two positions further on
-            if (tid == 0) issue_rings(min(ne, (r0 + 32) / A + 2));
+            if (tid == 0) issue_rings(min(ne, (r0 + 32) / A + NB));
             buf ^= 1;
         }
         ebase += ne;
@@ -247,10 +266,10 @@ static int launch_rt_w(StepParams& p, size_t smem, int grid, cudaStream_t s) {
 // about one env-time of per-group overhead: barriers and the un-overlapped step phase), and every CTA waits for the
 // slowest, so minimise ceil(ceil(E/g)/slots) * (g + 1).  Measured on 4,096 x 50 (config 2): g = 7 → 2 full rounds,
 // 58.6 us; the former power-of-two choice g = 4 → 3.46 → 4 rounds, 67.2 us.  Large batches end up at kRtGroup.
-static int pick_group(int E, int slots) {
+static int pick_group(int E, int slots, int gmax) {
     int best = 1;
     long best_cost = -1;
-    for (int g = kRtGroup; g >= 1; --g) {
+    for (int g = gmax; g >= 1; --g) {
         const long n = (E + g - 1) / g;
         const long rounds = (n + slots - 1) / slots;
         const long cost = rounds * (g + 1);
@@ -265,12 +284,20 @@ int pmrl_launch_step_obs_rt(StepParams& p, int npl, int group, int ctas_per_sm, 
     if ((size_t)p.A * p.T >= (1u << 31) || p.A >= 65536) return -100;
     const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : 2;
     const int slots = pmrl_sm_count() * per_sm;
-    int G = group > 0 ? group : pick_group(p.E, slots);
-    if (G > kRtGroup) G = kRtGroup;
+    const int gmax = npl <= 2 ? kRtGroupNarrow : kRtGroup;
+    int G = group > 0 ? group : pick_group(p.E, slots, gmax);
+    if (G > gmax) G = gmax;
     p.group_envs = G;
     p.tile_assets = 32;
-    const size_t smem = (size_t)2 * 32 * p.W * 5 * 4 + (size_t)2 * p.W * p.A * 4 + (size_t)G * p.A * 8;
-    if (smem > (size_t)(226 * 1024) / per_sm - 1024) return -100;
+    // ring buffers: a 32-row tile may touch two envs, and the ring of env n+NB can only be requested once env n is
+    // done — with two buffers a 50-asset env gets its ring one tile (≈2 us) before it is needed, less than a DRAM round
+    // trip under load.  Narrow envs have small rings: keep up to four resident.
+    const size_t budget = (size_t)(226 * 1024) / per_sm - 1024;
+    const size_t fixed = (size_t)2 * 32 * p.W * 5 * 4 + (size_t)G * p.A * 8, ring_bytes = (size_t)p.W * p.A * 4;
+    if (fixed + 2 * ring_bytes > budget) return -100;
+    int nb = (int)((budget - fixed) / ring_bytes);
+    p.ring_bufs = nb > 4 ? 4 : nb;
+    const size_t smem = fixed + (size_t)p.ring_bufs * ring_bytes;
     const int n_groups = (p.E + G - 1) / G;
     const int grid = n_groups < slots ? n_groups : slots;
     p.ticket = next_ticket_slot();

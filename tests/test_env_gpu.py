@@ -109,7 +109,7 @@ DEFAULT_TM = 0
 # fast fill, generic fill, warp-specialised TMA pipeline with 2..6 stages (tma=1), ring-through-TMA variant (tma=2), tensor-map TMA variant (tma=3))
 # and the two-kernel path
 VARIANTS = [(1, 0, 0, 0, 1), (1, 0, 3, 0, 1), (2, 8, 3, 0, 0), (2, 32, 1, 0, 0), (0, 0, 0, 0, 1),
-            (1, 0, 0, 1, 4), (1, 0, 2, 1, 2), (1, 0, 8, 1, 6), (1, 0, 0, 2, 1), (1, 0, 3, 2, 1), (1, 0, 5, 2, 1), (1, 0, 7, 2, 1),
+            (1, 0, 0, 1, 4), (1, 0, 2, 1, 2), (1, 0, 8, 1, 6), (1, 0, 0, 2, 1), (1, 0, 3, 2, 1), (1, 0, 5, 2, 1), (1, 0, 7, 2, 1), (1, 0, 12, 2, 1), (1, 0, 16, 2, 1),
             (1, 0, 0, 3, 1), (1, 0, 3, 3, 1)]
 
 
