@@ -1,14 +1,17 @@
 // env_step_rt.cu — fused step + observation kernel, variant "RT": the weight ring of an env enters the SM as ONE
 // contiguous TMA bulk load (W·A·4 bytes, e.g. 20 KB) instead of 8 register loads per thread and tile.
 //
-// Same structure as env_step_fast.cu (persistent CTAs, groups of G <= 8 envs, 32-asset-row tiles, register-staged
-// table loads, one TMA bulk store per tile) with these differences:
+// Same structure as env_step_fast.cu (persistent CTAs, groups of G <= 8 envs — 16 for A <= 64, two per warp —,
+// 32-asset-row tiles, register-staged table loads, one TMA bulk store per tile) with these differences:
 //   * ring rows never travel through registers or the L1 load queue: thread 0 issues cp.async.bulk global→shared for
 //     the whole ring of env el (2-4 rings resident: envs el .. el+NB-1), completion on an mbarrier; the weight
 //     channel of a tile is then filled from shared memory (lanes over assets: conflict-free).  The L1 queue only
 //     carries the L2-hit table loads, so no DRAM-latency load can sit in front of them, and DRAM sees one
 //     page-friendly 20 KB read per env instead of 200 scattered 128-byte reads;
-//   * 2 CTAs per SM (110 KB of shared memory each), up to 128 registers, no spills.
+//   * 2 CTAs per SM (110 KB of shared memory each), up to 128 registers, no spills;
+//   * groups are handed out through a self-resetting global ticket counter (no static stride: no 55-or-56-round tail,
+//     and a CTA delayed by a concurrent kernel just takes fewer groups); while a group streams, the next group's
+//     actions and scalar state are prefetched into L2.
 // Requires (W·A) % 4 == 0 (16-byte alignment of every env's ring) and 2·W·A·4 + tiles to fit in shared memory.
 // Weight channel semantics: ActionBuffer.get_all (weight_buffer.py:32-44), fresh row from shared memory.
 #include <cuda_runtime.h>
@@ -265,7 +268,8 @@ static int launch_rt_w(StepParams& p, size_t smem, int grid, cudaStream_t s) {
 // Envs per group for a batch of E envs on `slots` persistent CTAs.  A CTA's time is (rounds it runs) x (envs per group +
 // about one env-time of per-group overhead: barriers and the un-overlapped step phase), and every CTA waits for the
 // slowest, so minimise ceil(ceil(E/g)/slots) * (g + 1).  Measured on 4,096 x 50 (config 2): g = 7 → 2 full rounds,
-// 58.6 us; the former power-of-two choice g = 4 → 3.46 → 4 rounds, 67.2 us.  Large batches end up at kRtGroup.
+// 58.6 us; the former power-of-two choice g = 4 → 3.46 → 4 rounds, 67.2 us (with 16-env groups and four resident
+// rings: g = 14 → one round, 53.4 us).  Large batches end up at the maximum.
 static int pick_group(int E, int slots, int gmax) {
     int best = 1;
     long best_cost = -1;
