@@ -29,6 +29,7 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # name: (envs per GPU, assets, window, features, commission, obs materialised, description)
     "c4_shard": (131072, 100, 50, 5, 0.0, True, "BASELINE config 4 shard: 131,072 envs/GPU x 100 assets x window 50, obs materialised"),
+    "c4": (1048576, 100, 50, 5, 0.0, True, "BASELINE config 4 whole: 1,048,576 envs x 100 assets x window 50 divided over the ranks (strong scaling), obs materialised"),
     "c2": (4096, 50, 50, 5, 0.0, True, "BASELINE config 2: 4,096 envs x 50 assets x window 50, obs materialised"),
     "c2_state": (4096, 50, 50, 5, 0.0, False, "BASELINE config 2, state-only step (no obs)"),
     "c3": (65536, 100, 50, 5, 0.0, True, "BASELINE config 3: 65,536 envs x 100 assets, obs materialised"),
@@ -215,6 +216,9 @@ def main():
     E, A, W, F, commission, obs, desc = WORKLOADS[args.workload]
     if args.envs:
         E = args.envs
+    strong = args.workload == "c4" and not args.envs
+    if strong:                                                # config 4 whole: the 1,048,576 envs are divided over the ranks
+        E = E // world
     first_env = rank * E                                      # weak scaling: rank r owns global envs [r*E, (r+1)*E)
     tbl = synth.gbm_ohlc(TABLE_ROWS, A)
     t0 = synth.episode_offsets(E, TABLE_ROWS, W, EPISODE_LEN, first_env=first_env)
@@ -328,7 +332,7 @@ def main():
         line = {
             "metric": "asset_steps_per_s", "value": value, "unit": "asset-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "env_steps_per_s": value / A,
             "config": {"workload": args.workload, "description": desc, "envs_per_gpu": E, "envs_total": world * E,
                        "assets": A, "window": W, "features": F, "commission": commission, "obs_materialised": obs,

@@ -24,6 +24,7 @@ def test_workloads_are_the_baseline_configs():
     assert w["c2"][:3] == (4096, 50, 50) and w["c3"][:3] == (65536, 100, 50) and w["c5"][:3] == (262144, 500, 50)
     assert w["c4_shard"][0] * 8 == 1048576 and w["c4_shard"][1:3] == (100, 50)
     assert w["c5"][4] == 0.0025 and not w["c5"][5]                     # commission, state-only
+    assert w["c4"][:3] == (1048576, 100, 50)                           # config 4 whole (divided over the ranks: strong scaling)
 
 
 def test_reference_arm_prints_the_contract_line():
