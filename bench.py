@@ -184,7 +184,8 @@ def main():
                     help="env slices of the host-buffer step: >0 geometric x2.5, <0 equal, 0 library default (5 geometric)")
     ap.add_argument("--stats-every", type=int, default=1,
                     help="multi-GPU: all-reduce the stats vector over NCCL every K steps (SURVEY 8e: K = 1); 0 = only at the end")
-    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (launch-bound small batches)")
+    ap.add_argument("--graph", type=int, nargs="?", const=1, default=0, metavar="K",
+                    help="replay the step from a CUDA graph (launch-bound small batches); K > 1 captures K-step bursts in one graph")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VAL",
                     help="kernel launch-shape override: rows|group|ctas|fused|fast = int (pmrl_set_tuning)")
     args = ap.parse_args()
@@ -242,14 +243,20 @@ def main():
     stats_in_sync = None
 
     graph_launches_per_step = 0
+    burst = max(1, args.graph)
     if args.graph:
+        if args.steps % burst or args.warmup % burst:
+            args.steps = max(burst, args.steps // burst * burst)
+            args.warmup = max(burst, -(-args.warmup // burst) * burst)
         c0 = _lib.load().pmrl_launch_count()
-        static_actions, replay = env.graphed_step(obs=obs)
-        graph_launches_per_step = int(_lib.load().pmrl_launch_count() - c0) // 2     # one warm-up call + the captured call
+        static_actions, replay = env.graphed_step(obs=obs, steps=burst)
+        graph_launches_per_step = int(_lib.load().pmrl_launch_count() - c0) // (burst + 1)   # one warm-up step + the captured burst
+        burst_pool = [torch.stack([pool[(j + k) % n_pool] for k in range(burst)]) if burst > 1 else pool[j] for j in range(n_pool)]
 
-        def one_step(i):
-            static_actions.copy_(pool[i % n_pool])         # the policy would write its actions here
-            replay()
+        def one_step(i):                                      # called once per env step; a burst is replayed on its first step
+            if i % burst == 0:
+                static_actions.copy_(burst_pool[(i // burst) % n_pool])   # the policy would write its actions here
+                replay()
     else:
         def one_step(i):
             env.step(pool[i % n_pool], obs=obs)
@@ -336,7 +343,7 @@ def main():
             "env_steps_per_s": value / A,
             "config": {"workload": args.workload, "description": desc, "envs_per_gpu": E, "envs_total": world * E,
                        "assets": A, "window": W, "features": F, "commission": commission, "obs_materialised": obs,
-                       "episode_len": EPISODE_LEN, "table_rows": TABLE_ROWS, "preroll_steps": preroll, "tune": args.tune, "cuda_graph": bool(args.graph), "actions": "raw N(0,1) scores (softmax branch)",
+                       "episode_len": EPISODE_LEN, "table_rows": TABLE_ROWS, "preroll_steps": preroll, "tune": args.tune, "cuda_graph": bool(args.graph), "graph_burst_steps": burst if args.graph else None, "actions": "raw N(0,1) scores (softmax branch)",
                        "parallelism": f"env-shard x{world}, no data-path collective" + (", NCCL stats all-reduce every step (async)" if world > 1 else ""),
                        "l2_policy": "working set per step (obs write + ring) exceeds L2 (126 MB)" if E * A * W * 4 > 126e6
                                     else "working set smaller than L2: L2-resident by construction"},

@@ -116,7 +116,11 @@ def ptr(t) -> int | None:
 
 
 def current_stream() -> int:
+    """Raw handle of torch's current CUDA stream (the stream every entry point enqueues on)."""
     import torch
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:                       # ~0.2 us instead of ~2 us for the Stream object round trip
+        return raw(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -134,6 +134,7 @@ class BatchedTradingEnv:
                                        _lib.ptr(self.is_full), _lib.ptr(self.t), _lib.ptr(self.t0),
                                        _lib.ptr(self.sharpe), _lib.ptr(self.ep_return))
         self._p_cfg, self._p_tbl, self._p_st = C.byref(self._c_cfg), C.byref(self._c_tbl), C.byref(self._c_st)
+        self._ptr_reward, self._ptr_done, self._ptr_stats = _lib.ptr(self.reward), _lib.ptr(self.done), _lib.ptr(self._stats)
         self.reset(obs=False)
 
     # ------------------------------------------------------------------------------------------
@@ -166,18 +167,20 @@ class BatchedTradingEnv:
         relatives [E, A] (else computed from the close table).  Returns (obs | None, reward [E], done [E] u8);
         the returned tensors are the env's own buffers and are overwritten by the next step."""
         a = actions
-        if a.dtype != torch.float32 or not a.is_cuda:
-            a = a.to(device=self.device, dtype=torch.float32)
-        a = a.reshape(self.E, self.A).contiguous()
+        if not (a.is_cuda and a.dtype is torch.float32 and a.is_contiguous() and a.numel() == self.E * self.A):   # else: hot path, no torch ops
+            if a.dtype != torch.float32 or not a.is_cuda:
+                a = a.to(device=self.device, dtype=torch.float32)
+            a = a.reshape(self.E, self.A).contiguous()
         if y is not None:
             y = y.to(device=self.device, dtype=torch.float32).reshape(self.E, self.A).contiguous()
         want_obs = obs and self.feat_am is not None
         buf = self._obs_buffer(out) if want_obs else None
         rc = self.lib.pmrl_env_step(self._p_cfg, self._p_tbl, self._p_st, a.data_ptr(), _lib.ptr(y),
-                                    self.reward.data_ptr(), self.done.data_ptr(), _lib.ptr(buf),
-                                    OBS_FULL if want_obs else OBS_NONE, _lib.ptr(self._stats),
+                                    self._ptr_reward, self._ptr_done, buf.data_ptr() if buf is not None else None,
+                                    OBS_FULL if want_obs else OBS_NONE, self._ptr_stats,
                                     _lib.current_stream())
-        _lib.check(rc, "pmrl_env_step")
+        if rc:
+            _lib.check(rc, "pmrl_env_step")
         return buf, self.reward, self.done
 
     # ------------------------------------------------------------------------------------------
@@ -211,27 +214,47 @@ class BatchedTradingEnv:
         _lib.check(rc, "pmrl_env_step_host")
         return buf, reward_host, done_host
 
-    def graphed_step(self, obs: bool = True, out=None):
-        """Capture one step in a CUDA graph (launch-bound small batches: 4,096 x 50 moves 1.7 MB per state-only step).
-        Returns (static_actions [E, A], replay) — fill `static_actions` in place, then call `replay()` which
-        returns the same (obs, reward, done) buffers as `step`.  The kernels take no host-side decisions after
-        validation, so the captured launch is valid for every later step (auto-resets included)."""
-        static_actions = torch.zeros(self.E, self.A, dtype=torch.float32, device=self.device)
+    def graphed_step(self, obs: bool = True, out=None, steps: int = 1):
+        """Capture `steps` consecutive steps in ONE CUDA graph (launch-bound small batches: 4,096 x 50 moves 1.7 MB per
+        state-only step; imagination rollouts advance in fixed bursts, cf. HORIZON = 15 in config/dreamer.py:54).
+        Returns (static_actions, replay): fill `static_actions` ([E, A] for steps == 1, else [steps, E, A]) in place, then
+        call `replay()`, which returns (obs, reward, done) like `step` — for steps > 1 reward and done are [steps, E]
+        (one row per captured step; the obs buffer is rewritten by every step and holds the last one).  The kernels take no host-side decisions after
+        validation, so the captured launches are valid for every later burst (auto-resets included).  Replays of one
+        captured graph must not overlap each other (they share these static buffers)."""
+        K = int(steps)
+        if K < 1:
+            raise ValueError("steps must be >= 1")
+        shape = (self.E, self.A) if K == 1 else (K, self.E, self.A)
+        static_actions = torch.zeros(*shape, dtype=torch.float32, device=self.device)
+        acts = [static_actions] if K == 1 else [static_actions[k] for k in range(K)]
+        rew = torch.zeros(K, self.E, dtype=torch.float32, device=self.device) if K > 1 else None
+        dn = torch.zeros(K, self.E, dtype=torch.uint8, device=self.device) if K > 1 else None
+        state = (self.value, self.hist, self.idx, self.is_full, self.t, self.ep_return) + ((self.sharpe,) if self.sharpe is not None else ())
+
+        def burst():
+            res = None
+            for k in range(K):
+                res = self.step(acts[k], obs=obs, out=out)
+                if K > 1:
+                    rew[k].copy_(res[1]); dn[k].copy_(res[2])
+            return res if K == 1 else (res[0], rew, dn)
+
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):                        # warm-up launch outside capture (lazy module loading, smem attributes)
-            snap = [t.clone() for t in (self.value, self.hist, self.idx, self.is_full, self.t, self.ep_return)]
+            snap = [t.clone() for t in state]
             stats_snap = self._stats.clone() if self._stats is not None else None
-            self.step(static_actions, obs=obs, out=out)
-            for dst, src in zip((self.value, self.hist, self.idx, self.is_full, self.t, self.ep_return), snap):
+            self.step(acts[0], obs=obs, out=out)
+            for dst, src in zip(state, snap):
                 dst.copy_(src)                            # undo the warm-up transition
             if stats_snap is not None:
                 self._stats.copy_(stats_snap)
         torch.cuda.current_stream(self.device).wait_stream(s)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            result = self.step(static_actions, obs=obs, out=out)
-        for dst, src in zip((self.value, self.hist, self.idx, self.is_full, self.t, self.ep_return), snap):
+            result = burst()
+        for dst, src in zip(state, snap):
             dst.copy_(src)                                # capture does not execute, but keep the state explicit
         if stats_snap is not None:
             self._stats.copy_(stats_snap)

@@ -450,6 +450,30 @@ def test_graphed_step_matches_eager():
     compare_obs(obs, ora, "end")
 
 
+@pytest.mark.parametrize("obs", [False, True])
+def test_graphed_burst_of_steps_matches_eager(obs):
+    """graphed_step(steps=K): K transitions captured in one CUDA graph give the state, rewards and dones of K eager steps
+    (episode end and auto-reset inside a burst included)."""
+    E, A, W, L, K = 37, 40, 8, 11, 5
+    g_env, _ = make_pair(E, A, W, 5, episode_len=L, collect_stats=True)
+    e_env, _ = make_pair(E, A, W, 5, episode_len=L, collect_stats=True)
+    g_env.reset(obs=obs); e_env.reset(obs=obs)
+    static_actions, replay = g_env.graphed_step(obs=obs, steps=K)
+    assert static_actions.shape == (K, E, A)
+    gen = torch.Generator().manual_seed(9)
+    for b in range(4):                                     # 20 steps: crosses the episode end (11) and the auto-reset call
+        acts = torch.randn(K, E, A, generator=gen).cuda()
+        static_actions.copy_(acts)
+        o_g, r_g, d_g = replay()
+        for k in range(K):
+            o_e, r_e, d_e = e_env.step(acts[k], obs=obs)
+            assert torch.equal(r_g[k], r_e) and torch.equal(d_g[k], d_e), f"burst {b} step {k}"
+        assert torch.equal(g_env.value, e_env.value) and torch.equal(g_env.hist, e_env.hist) and torch.equal(g_env.t, e_env.t)
+        if obs:
+            assert torch.equal(o_g, o_e)
+    assert g_env.stats()["n_envs"] == e_env.stats()["n_envs"]
+
+
 def test_window_of_one_is_rejected_like_the_reference_would_fail():
     pmrl, synth, Env = _mods()
     with pytest.raises(ValueError):
