@@ -10,7 +10,10 @@ and `agent/pg` drive it unchanged:
 
 `features` / `prices` are supplied by the caller exactly as in the reference (the loader owns the
 windows), so the kernels run with external price relatives and only write the weight channel
-(PMRL_OBS_WEIGHTS).  CPU tensors are staged through the device; there is no CPU compute path.
+(PMRL_OBS_WEIGHTS).  There is no CPU compute path.  A caller that keeps everything on the CPU (the reference's own loop)
+goes through page-locked staging buffers: action and price relatives are copied into pinned memory the kernels read in
+place, reward / done / weight channel are written by the kernels straight into pinned memory, and one stream
+synchronisation per step makes them host tensors — no per-step torch H2D/D2H ops.
 """
 from __future__ import annotations
 
@@ -19,7 +22,7 @@ import torch
 
 from . import _lib
 from .config import EnvConfig
-from .env import BatchedTradingEnv
+from .env import BatchedTradingEnv, OBS_NONE, OBS_WEIGHTS
 
 
 class _WeightsView:
@@ -99,7 +102,60 @@ class TradingEnv:
         self.weights = _WeightsView(self)
         self.reward = _RewardView(self)
         self._trace = None
+        self._pin = None                                  # page-locked staging of the CPU-caller path, made on first use
+        self._host_idx = 1                                # ring slot the next step writes (E = 1: known on the host)
         self._clear_trace()
+
+    def _pinned(self):
+        if self._pin is None:
+            e = self._env
+            A, W, F = e.A, e.W, e.F
+            p = {"in": torch.zeros(2, A).pin_memory(), "obs": torch.zeros(1, A, W, F).pin_memory(),
+                 "r": torch.zeros(1).pin_memory(), "d": torch.zeros(1, dtype=torch.uint8).pin_memory(),
+                 "v": torch.zeros(1).pin_memory(), "w": torch.zeros(A).pin_memory()}
+            p["ptr_a"], p["ptr_y"] = p["in"][0].data_ptr(), p["in"][1].data_ptr()   # device-addressable under unified addressing
+            p["ptr_obs"], p["ptr_r"], p["ptr_d"] = p["obs"].data_ptr(), p["r"].data_ptr(), p["d"].data_ptr()
+            p["v_prev"] = torch.full((), float(self.cfg.initial_cash))
+            self._pin = p
+        return self._pin
+
+    def _weights_to_host(self, features):
+        """features[:, :, -1] = get_all() for a CPU `features`: the WEIGHTS-mode kernel writes the channel into a pinned
+        scratch obs (posted writes over PCIe), the host copies the strided channel after the caller's synchronisation."""
+        e, p = self._env, self._pinned()
+        rc = e.lib.pmrl_obs_build(e._p_cfg, e._p_tbl, e._p_st, p["ptr_obs"], OBS_WEIGHTS, _lib.current_stream())
+        if rc:
+            _lib.check(rc, "pmrl_obs_build")
+
+    def _step_host(self, action, features, prices):
+        e, p = self._env, self._pinned()
+        A, W, F = e.A, e.W, e.F
+        if tuple(features.shape[-3:]) != (A, W, F):
+            raise ValueError(f"features must be [{A}, {W}, {F}], got {tuple(features.shape)}")
+        p["in"][0].copy_(action.reshape(A))
+        p["in"][1].copy_(prices.reshape(A))
+        stream = _lib.current_stream()
+        rc = e.lib.pmrl_env_step(e._p_cfg, e._p_tbl, e._p_st, p["ptr_a"], p["ptr_y"], p["ptr_r"], p["ptr_d"], None,
+                                 OBS_NONE, e._ptr_stats, stream)
+        if rc:
+            _lib.check(rc, "pmrl_env_step")
+        self._weights_to_host(features)
+        slot = self._host_idx
+        p["v"].copy_(e.value, non_blocking=True)
+        p["w"].copy_(e.hist[0, slot], non_blocking=True)
+        torch.cuda.current_stream(e.device).synchronize()
+        self._host_idx = (slot + 1) % W
+        v, r = p["v"][0].clone(), p["r"][0].clone()
+        t = self._trace
+        t["values"].append(v)
+        t["actions"].append(p["w"].clone())
+        t["rewards"].append(r)
+        t["returns"].append(v / p["v_prev"] if self.cfg.commission == 0 else torch.exp(r / self.cfg.reward_scale))
+        p["v_prev"] = v
+        features[..., -1] = p["obs"][0, :, :, -1]
+        if self.three_tuple:
+            return features, r, p["d"][0].clone()
+        return r, features
 
     # -- info: the reference appends host copies every step (:80,85,90,100); here the trace stays on the
     #    device and is materialised only when `info` is read --
@@ -107,13 +163,20 @@ class TradingEnv:
         self._trace = {"values": [], "actions": [], "rewards": [], "returns": []}
         self._first_action = self._env.weights_last[0].clone()
 
+    @staticmethod
+    def _stack(items):
+        """One host tensor from a trace list (entries are CUDA tensors for CUDA callers, CPU tensors for CPU callers)."""
+        if len({x.device for x in items}) == 1:
+            return torch.stack(items).cpu()
+        return torch.stack([x.cpu() for x in items])
+
     @property
     def info(self):
         t = self._trace
-        vals = [float(self.cfg.initial_cash)] + ([] if not t["values"] else torch.stack(t["values"]).cpu().tolist())
-        acts = [self._first_action.cpu().numpy()] + [a for a in (torch.stack(t["actions"]).cpu().numpy() if t["actions"] else [])]
-        rews = [0] + ([] if not t["rewards"] else torch.stack(t["rewards"]).cpu().tolist())
-        rets = [0] + ([] if not t["returns"] else torch.stack(t["returns"]).cpu().tolist())
+        vals = [float(self.cfg.initial_cash)] + ([] if not t["values"] else self._stack(t["values"]).tolist())
+        acts = [self._first_action.cpu().numpy()] + [a for a in (self._stack(t["actions"]).numpy() if t["actions"] else [])]
+        rews = [0] + ([] if not t["rewards"] else self._stack(t["rewards"]).tolist())
+        rets = [0] + ([] if not t["returns"] else self._stack(t["returns"]).tolist())
         return {"values": vals, "actions": acts, "rewards": rews, "returns": rets}
 
     @property
@@ -126,6 +189,10 @@ class TradingEnv:
             raise ValueError(f"features must be [{A}, {W}, {F}], got {tuple(features.shape)}")
         if features.is_cuda and features.dtype == torch.float32 and features.is_contiguous():
             self._env.write_weight_channel(features.view(1, A, W, F))
+        elif not features.is_cuda:
+            self._weights_to_host(features)
+            torch.cuda.current_stream(self._env.device).synchronize()
+            features[..., -1] = self._pinned()["obs"][0, :, :, -1]
         else:
             dev = features.to(device=self._env.device, dtype=torch.float32).contiguous().view(1, A, W, F)
             self._env.write_weight_channel(dev)
@@ -136,6 +203,9 @@ class TradingEnv:
         """trading_env.py:21-41."""
         self._env.reset(obs=False)
         self._clear_trace()
+        self._host_idx = 1
+        if self._pin is not None:
+            self._pin["v_prev"] = torch.full((), float(self.cfg.initial_cash))
         return self._write_weights(features)
 
     def step(self, action, features, prices):
@@ -143,6 +213,8 @@ class TradingEnv:
         A = self._env.A
         if action.numel() != A:
             raise ValueError(f"Action must have shape ({A},), got {tuple(action.shape)}")    # weight_buffer.py:18-19
+        if not (action.is_cuda or features.is_cuda or prices.is_cuda):
+            return self._step_host(action, features, prices)
         v_before = self._env.value.clone()
         _, r, done = self._env.step(action.reshape(1, A), y=prices.reshape(1, A), obs=False)
         t = self._trace
