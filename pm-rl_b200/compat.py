@@ -115,7 +115,6 @@ class TradingEnv:
                  "v": torch.zeros(1).pin_memory(), "w": torch.zeros(A).pin_memory()}
             p["ptr_a"], p["ptr_y"] = p["in"][0].data_ptr(), p["in"][1].data_ptr()   # device-addressable under unified addressing
             p["ptr_obs"], p["ptr_r"], p["ptr_d"] = p["obs"].data_ptr(), p["r"].data_ptr(), p["d"].data_ptr()
-            p["v_prev"] = torch.full((), float(self.cfg.initial_cash))
             self._pin = p
         return self._pin
 
@@ -150,8 +149,10 @@ class TradingEnv:
         t["values"].append(v)
         t["actions"].append(p["w"].clone())
         t["rewards"].append(r)
-        t["returns"].append(v / p["v_prev"] if self.cfg.commission == 0 else torch.exp(r / self.cfg.reward_scale))
-        p["v_prev"] = v
+        v_before = t["values"][-2] if len(t["values"]) > 1 else self.cfg.initial_cash
+        if not isinstance(v_before, float) and v_before.is_cuda:
+            v_before = v_before.cpu()
+        t["returns"].append(v / v_before if self.cfg.commission == 0 else torch.exp(r / self.cfg.reward_scale))
         features[..., -1] = p["obs"][0, :, :, -1]
         if self.three_tuple:
             return features, r, p["d"][0].clone()
@@ -204,8 +205,6 @@ class TradingEnv:
         self._env.reset(obs=False)
         self._clear_trace()
         self._host_idx = 1
-        if self._pin is not None:
-            self._pin["v_prev"] = torch.full((), float(self.cfg.initial_cash))
         return self._write_weights(features)
 
     def step(self, action, features, prices):
@@ -215,15 +214,30 @@ class TradingEnv:
             raise ValueError(f"Action must have shape ({A},), got {tuple(action.shape)}")    # weight_buffer.py:18-19
         if not (action.is_cuda or features.is_cuda or prices.is_cuda):
             return self._step_host(action, features, prices)
-        v_before = self._env.value.clone()
-        _, r, done = self._env.step(action.reshape(1, A), y=prices.reshape(1, A), obs=False)
+        e = self._env
+        fast = (action.is_cuda and prices.is_cuda and action.dtype is torch.float32 and prices.dtype is torch.float32
+                and action.is_contiguous() and prices.is_contiguous() and prices.numel() == A)
+        if fast:                                           # device tensors as they are: no torch ops before the launch
+            rc = e.lib.pmrl_env_step(e._p_cfg, e._p_tbl, e._p_st, action.data_ptr(), prices.data_ptr(), e._ptr_reward, e._ptr_done,
+                                     None, OBS_NONE, e._ptr_stats, _lib.current_stream())
+            if rc:
+                _lib.check(rc, "pmrl_env_step")
+            r, done = e.reward, e.done
+        else:
+            _, r, done = e.step(action.reshape(1, A), y=prices.reshape(1, A), obs=False)
+        slot = self._host_idx                              # E = 1, no auto-reset: the ring pointer is known on the host
+        self._host_idx = (slot + 1) % e.W
         t = self._trace
-        t["values"].append(self._env.value[0].clone())
-        t["actions"].append(self._env.weights_last[0].clone())
-        t["rewards"].append(r[0].clone())
-        t["returns"].append((self._env.value / v_before)[0] if self.cfg.commission == 0 else torch.exp(r[0] / self.cfg.reward_scale))
-        features = self._write_weights(features)
+        v = e.value[0].clone()
         rr = r[0].clone()
+        v_before = t["values"][-1] if t["values"] else self.cfg.initial_cash
+        if not isinstance(v_before, float) and v_before.device != v.device:
+            v_before = v_before.to(v.device)
+        t["values"].append(v)
+        t["actions"].append(e.hist[0, slot].clone())
+        t["rewards"].append(rr)
+        t["returns"].append(v / v_before if self.cfg.commission == 0 else torch.exp(rr / self.cfg.reward_scale))
+        features = self._write_weights(features)
         if self.three_tuple:
             return features, rr, done[0].clone()
         return rr, features
