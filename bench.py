@@ -186,6 +186,8 @@ def main():
                     help="multi-GPU: all-reduce the stats vector over NCCL every K steps (SURVEY 8e: K = 1); 0 = only at the end")
     ap.add_argument("--graph", type=int, nargs="?", const=1, default=0, metavar="K",
                     help="replay the step from a CUDA graph (launch-bound small batches); K > 1 captures K-step bursts in one graph")
+    ap.add_argument("--burst", type=int, default=0, metavar="K",
+                    help="state-only workloads: advance K steps per launch through pmrl_env_step_burst (imagination bursts)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VAL",
                     help="kernel launch-shape override: rows|group|ctas|fused|fast = int (pmrl_set_tuning)")
     args = ap.parse_args()
@@ -206,8 +208,8 @@ def main():
 
     rank, world, local_rank = pdist.init_from_env()
     from pmrl_b200 import _lib
-    tune_keys = {"rows": _lib.TUNE_TILE_ROWS, "group": _lib.TUNE_GROUP_ENVS, "ctas": _lib.TUNE_CTAS_PER_SM,
-                 "fused": _lib.TUNE_FUSED, "fast": _lib.TUNE_FAST_FILL, "tma": _lib.TUNE_TMA_PIPELINE, "stages": _lib.TUNE_TMA_STAGES, "var": _lib.TUNE_FAST_VARIANT, "rt": _lib.TUNE_RING_TMA, "tm": _lib.TUNE_TENSORMAP}
+    tune_keys = {"group": _lib.TUNE_GROUP_ENVS, "ctas": _lib.TUNE_CTAS_PER_SM, "fused": _lib.TUNE_FUSED,
+                 "fast": _lib.TUNE_FAST_FILL, "rt": _lib.TUNE_RING_TMA}
     for kv in args.tune:
         k, v = kv.split("=")
         _lib.set_tuning(tune_keys[k], int(v))
@@ -257,6 +259,19 @@ def main():
             if i % burst == 0:
                 static_actions.copy_(burst_pool[(i // burst) % n_pool])   # the policy would write its actions here
                 replay()
+    elif args.burst:
+        burst = args.burst
+        if obs:
+            raise SystemExit("--burst is a state-only mode")
+        args.steps = max(burst, args.steps // burst * burst)
+        args.warmup = max(burst, -(-args.warmup // burst) * burst)
+        burst_pool = [torch.stack([pool[(j + k) % n_pool] for k in range(burst)]) for j in range(n_pool)]
+        b_rew = torch.empty(burst, E, dtype=torch.float32, device=dev)
+        b_done = torch.empty(burst, E, dtype=torch.uint8, device=dev)
+
+        def one_step(i):
+            if i % burst == 0:
+                env.step_burst(burst_pool[(i // burst) % n_pool], b_rew, b_done)
     else:
         def one_step(i):
             env.step(pool[i % n_pool], obs=obs)
@@ -343,7 +358,7 @@ def main():
             "env_steps_per_s": value / A,
             "config": {"workload": args.workload, "description": desc, "envs_per_gpu": E, "envs_total": world * E,
                        "assets": A, "window": W, "features": F, "commission": commission, "obs_materialised": obs,
-                       "episode_len": EPISODE_LEN, "table_rows": TABLE_ROWS, "preroll_steps": preroll, "tune": args.tune, "cuda_graph": bool(args.graph), "graph_burst_steps": burst if args.graph else None, "actions": "raw N(0,1) scores (softmax branch)",
+                       "episode_len": EPISODE_LEN, "table_rows": TABLE_ROWS, "preroll_steps": preroll, "tune": args.tune, "cuda_graph": bool(args.graph), "graph_burst_steps": burst if args.graph else None, "burst_kernel_steps": args.burst or None, "actions": "raw N(0,1) scores (softmax branch)",
                        "parallelism": f"env-shard x{world}, no data-path collective" + (", NCCL stats all-reduce every step (async)" if world > 1 else ""),
                        "l2_policy": "working set per step (obs write + ring) exceeds L2 (126 MB)" if E * A * W * 4 > 126e6
                                     else "working set smaller than L2: L2-resident by construction"},

@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define PMRL_ABI_VERSION 2   /* 2: PmrlTables carries the price-relative table; pmrl_env_step_host, pmrl_price_relatives */
+#define PMRL_ABI_VERSION 3   /* 3: PmrlEnvState.ticket, PmrlStepIO + pmrl_env_step_io, pmrl_env_step_burst, pmrl_rollout_gather_index */
 
 /* error codes (negative) */
 #define PMRL_E_ARG        (-1)   /* null pointer / bad enum */
@@ -102,7 +102,35 @@ typedef struct PmrlEnvState {
     const int32_t* t0;         /* [E] (may be NULL when y_ext is used and obs_mode != FULL) */
     double*   sharpe;          /* [E, 3] running (n, mean, M2) of gross returns; required for PMRL_REWARD_SHARPE */
     float*    ep_return;       /* [E] running sum of rewards in the episode; required when stats != NULL */
+    uint32_t* ticket;          /* [2] zero-initialised work counters of THIS env batch ({next env group, CTAs finished}; the fused
+                                  step+obs kernel hands its env groups out through them and re-zeroes them before it exits), or
+                                  NULL → static group stride.  Owned by the batch, not by the library, so launches of different
+                                  env batches on different streams (eager or inside captured graphs) never share a counter;
+                                  launches of ONE batch must be stream-ordered anyway (they update the same state). */
 } PmrlEnvState;
+
+/* Per-step inputs / outputs of pmrl_env_step_io.  Zero-initialise, then set what is used. */
+typedef struct PmrlStepIO {
+    const float* actions;      /* [E, A] raw scores or weights */
+    const float* y_ext;        /* [E, A] external price relatives or NULL → table row t0+k+W-1 */
+    float*    reward;          /* [E] out */
+    uint8_t*  done;            /* [E] out */
+    float*    obs;             /* [E, A, W, F] out (FULL), in/out (WEIGHTS), NULL (NONE) */
+    int32_t   obs_mode;        /* PMRL_OBS_* */
+    double*   stats;           /* [PMRL_STATS_LEN] or NULL */
+    /* optional sinks: rows of a rollout / replay buffer slot written by the step kernel itself instead of by a separate
+     * copy (replay/rollout_buffer.py:51-57 stores a, v, r; replay/buffer.py:31-37 stores i, a, r) — `reward` may point
+     * straight at the r row of the slot, `obs` at s[slot + 1] */
+    float*    action_sink;     /* [E, A] raw action as received */
+    float*    value_sink;      /* [E] portfolio value after the step (train/on_policy.py:65 stores env.value) */
+    float*    weight_sink;     /* [E, A] post-drift weights w' of this step: the un-wrapped weight history an index-mode rollout
+                                  buffer regenerates the obs weight channel from (pmrl_rollout_gather_index) */
+    int32_t*  index_sink;      /* [E] loader item index t0 + k of this step (train/off_policy.py:87) */
+    /* optional host mirrors: device-visible addresses of page-locked mapped host memory (cudaHostGetDevicePointer);
+     * the kernel writes reward / done there as well (posted PCIe writes), so a host caller needs no D2H copy */
+    float*    reward_host;     /* [E] or NULL */
+    uint8_t*  done_host;       /* [E] or NULL (set together with reward_host) */
+} PmrlStepIO;
 
 /* stats vector written by pmrl_env_step (accumulated with atomics; caller zeroes it) */
 #define PMRL_STATS_LEN 10
@@ -118,22 +146,22 @@ typedef struct PmrlEnvState {
 #define PMRL_STAT_MAX_NEGV   9   /* max −V  (caller initialises to -inf) → min V = −this */
 
 int         pmrl_abi_version(void);
+/* sizeof of a boundary struct as compiled into the library (0 PmrlEnvCfg, 1 PmrlTables, 2 PmrlEnvState, 3 PmrlStepIO; 100+:
+ * selected field offsets) — lets a foreign-language binding verify its mirror of the structs; -1 for an unknown code. */
+int         pmrl_abi_sizeof(int32_t which);
 const char* pmrl_last_error(void);
 
 /* Launch-shape tuning hook (process-wide; for benchmarking the kernel variants, not part of the reference surface).
  * value <= 0 restores the built-in heuristic. */
-#define PMRL_TUNE_TILE_ROWS   1   /* asset-rows per obs tile of the fused kernel (power of two <= 32) */
-#define PMRL_TUNE_GROUP_ENVS  2   /* envs a CTA advances together (1..8) */
+#define PMRL_TUNE_GROUP_ENVS  2   /* envs a CTA advances together (1..16) */
 #define PMRL_TUNE_CTAS_PER_SM 3   /* persistent CTAs per SM */
-#define PMRL_TUNE_FUSED       4   /* 1 (default): fused step+obs kernel where a specialised one covers the shape, else k_env_step
-                                     followed by k_obs_build; 0: always the two kernels; 2: as 1 but the generic fused kernel
-                                     instead of the two-kernel fallback */
-#define PMRL_TUNE_FAST_FILL   5   /* 1 (default): specialised kernels (register-staged fill / TMA pipeline) when F == 5 && W <= 64 */
-#define PMRL_TUNE_TMA_PIPELINE 8  /* 1: warp-specialised TMA-load pipeline variant of the fused kernel (F == 5, W <= 64, A <= 512) */
-#define PMRL_TUNE_TMA_STAGES  9   /* staging buffers of that variant (2..6) */
-#define PMRL_TUNE_RING_TMA    11  /* 1 (default): fused kernel that loads each env's weight ring with one TMA bulk copy (env_step_rt.cu); 0: register ring loads (env_step_fast.cu) */
-#define PMRL_TUNE_TENSORMAP   12  /* 1: fused kernel variant whose feature windows arrive as tensor-map TMA boxes (env_step_tm.cu) */
-#define PMRL_TUNE_FAST_VARIANT 10 /* code-generation variant mask of the register-staged kernel (A/B measurement; see env_step_fast.cu) */
+#define PMRL_TUNE_FUSED       4   /* 1 (default): fused step+obs kernel where one covers the shape, else k_env_step followed by the
+                                     obs tile kernel; 0: always the two kernels */
+#define PMRL_TUNE_FAST_FILL   5   /* 1 (default): specialised obs kernels (fused RT / register-staged, division-free tile fill);
+                                     0: generic k_obs_build after the state-only step */
+#define PMRL_TUNE_RING_TMA    11  /* 1 (default): fused kernel that loads each env's weight ring with one TMA bulk copy
+                                     (env_step_rt.cu); 2: the same without the next-group L2 prefetch; 0: register ring loads
+                                     (env_step_fast.cu) */
 int pmrl_set_tuning(int32_t key, int32_t value);
 
 /* Kernels this library has launched in this process so far (every entry point counts its own launches; bench.py reports
@@ -159,6 +187,18 @@ int pmrl_env_step(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvSta
                   const float* actions, const float* y_ext,
                   float* reward, uint8_t* done, float* obs, int32_t obs_mode,
                   double* stats, void* stream);
+
+/* The same transition with the optional sinks / host mirrors of PmrlStepIO (pmrl_env_step is this call with none set). */
+int pmrl_env_step_io(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
+                     const PmrlStepIO* io, void* stream);
+
+/* K consecutive state-only transitions in ONE launch on pre-supplied actions — imagination rollouts advance in fixed
+ * bursts (HORIZON = 15, config/dreamer.py:54; agent/dreamer/dreamer.py:104-158).  actions [K, E, A], reward [K, E],
+ * done [K, E]; price relatives come from tbl->y_tm.  Bit-identical to K calls of pmrl_env_step with obs_mode NONE
+ * (auto-resets included); each env's scalar state and newest weight row stay in registers across the burst. */
+int pmrl_env_step_burst(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
+                        const float* actions, int32_t K, float* reward, uint8_t* done,
+                        double* stats, void* stream);
 
 /* The same transition driven from HOST buffers — the call the reference's loop makes with CPU tensors
  * (`r, obs = env.step(action, …)` then `env.value` read on the host, train/on_policy.py:64-65).
@@ -216,8 +256,7 @@ int pmrl_pack_features(const float* series, const float* close, int32_t A, int32
  * fp32 with NaN over each indicator's lookback — TA-Lib is not vendored: parity UNPINNED).
  * specs: HOST array [n_specs, 2] of (PMRL_IND_*, period); series [A*C, L] with channels o,h,l,c[,v] (index a*C + c);
  * out [A, n_out, L] where n_out / the maximum lookback come from pmrl_indicator_layout (BBANDS: upper, middle, lower;
- * MACD 12/26/9: macd, signal, hist; STOCH 5/3/3: slowk, slowd; the others one output).  ADX / DX of the reference's
- * commented default list are not implemented (their TA-Lib seeding cannot be verified here). */
+ * MACD 12/26/9: macd, signal, hist; STOCH 5/3/3: slowk, slowd; the others one output). */
 #define PMRL_IND_SMA    0
 #define PMRL_IND_EMA    1
 #define PMRL_IND_RSI    2
@@ -251,6 +290,19 @@ int pmrl_rollout_gather(int32_t S, int32_t E, int32_t A, int32_t W, int32_t F, i
                         const float* s, const float* a, const float* v, const float* r, const float* y,
                         float* s_out, float* a_out, float* r_out, float* pv_out, float* pa_out, float* p_out,
                         void* stream);
+
+/* The same minibatch from an INDEX-mode rollout buffer, which stores per slot only bi [S, E] i32 (loader item index t0 + n of
+ * the step, PmrlStepIO.index_sink), a [S, E, A], v [S, E], r [S, E] plus the un-wrapped weight history wp [S + W - 1, E, A]
+ * (wp[m] = w' after step m, PmrlStepIO.weight_sink; wp[0] = all-cash): s_out[b] is regenerated — rows [i-1, i-1+W) of feat_am
+ * and the ring-ordered weight channel of ActionBuffer.get_all (weight_buffer.py:38-39) from wp — like ReplayBuffer.sample
+ * regenerates its windows (replay/buffer.py:58-77); p_out[b] = y_tm[i + W - 1].  8·A + 12 bytes per env-step of storage
+ * instead of 4·A·W·F.  Slots are >= 1 (slot - 1 is read, rollout_buffer.py:130-131). */
+int pmrl_rollout_gather_index(int32_t S, int32_t E, int32_t A, int32_t W, int32_t F, int32_t T, int32_t B,
+                              const int32_t* slots, const int32_t* envs,
+                              const int32_t* bi, const float* a, const float* v, const float* r,
+                              const float* wp, const float* feat_am, const float* y_tm,
+                              float* s_out, float* a_out, float* r_out, float* pv_out, float* pa_out, float* p_out,
+                              void* stream);
 
 /* Off-policy index replay: store (i, a, r) of all E envs at [epoch_slot, step_slot] (buffer.py:31-37).
  * Buffers: bi [P, L, E] i32, ba [P, L, E, A], br [P, L, E]. */

@@ -29,19 +29,29 @@ class PmrlTables(C.Structure):
 
 class PmrlEnvState(C.Structure):
     _fields_ = [("value", c_void_p), ("hist", c_void_p), ("idx", c_void_p), ("is_full", c_void_p),
-                ("t", c_void_p), ("t0", c_void_p), ("sharpe", c_void_p), ("ep_return", c_void_p)]
+                ("t", c_void_p), ("t0", c_void_p), ("sharpe", c_void_p), ("ep_return", c_void_p), ("ticket", c_void_p)]
+
+
+class PmrlStepIO(C.Structure):
+    _fields_ = [("actions", c_void_p), ("y_ext", c_void_p), ("reward", c_void_p), ("done", c_void_p), ("obs", c_void_p),
+                ("obs_mode", i32), ("stats", c_void_p), ("action_sink", c_void_p), ("value_sink", c_void_p),
+                ("weight_sink", c_void_p), ("index_sink", c_void_p), ("reward_host", c_void_p), ("done_host", c_void_p)]
 
 
 P = C.POINTER
 # symbol → (restype, argtypes); must list every function declared in include/pmrl_b200.h
 SIGNATURES = {
     "pmrl_abi_version": (C.c_int, []),
+    "pmrl_abi_sizeof": (C.c_int, [i32]),
     "pmrl_launch_count": (C.c_uint64, []),
     "pmrl_last_error": (C.c_char_p, []),
     "pmrl_set_tuning": (C.c_int, [i32, i32]),
     "pmrl_env_reset": (C.c_int, [P(PmrlEnvCfg), P(PmrlTables), P(PmrlEnvState), c_void_p, c_void_p, i32, c_void_p]),
     "pmrl_env_step": (C.c_int, [P(PmrlEnvCfg), P(PmrlTables), P(PmrlEnvState), c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, i32, c_void_p, c_void_p]),
+    "pmrl_env_step_io": (C.c_int, [P(PmrlEnvCfg), P(PmrlTables), P(PmrlEnvState), P(PmrlStepIO), c_void_p]),
+    "pmrl_env_step_burst": (C.c_int, [P(PmrlEnvCfg), P(PmrlTables), P(PmrlEnvState), c_void_p, i32, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
     "pmrl_env_step_host": (C.c_int, [P(PmrlEnvCfg), P(PmrlTables), P(PmrlEnvState), c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, i32, c_void_p, i32, c_void_p]),
     "pmrl_price_relatives": (C.c_int, [c_void_p, i32, i32, c_void_p, c_void_p]),
@@ -58,6 +68,9 @@ SIGNATURES = {
     "pmrl_rollout_gather": (C.c_int, [i32, i32, i32, i32, i32, i32, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pmrl_rollout_gather_index": (C.c_int, [i32, i32, i32, i32, i32, i32, i32, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pmrl_replay_add": (C.c_int, [i32, i32, i32, i32, i32, i32, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "pmrl_replay_gather": (C.c_int, [i32, i32, i32, i32, i32, i32, i32, i32, c_void_p, c_void_p, c_void_p,
@@ -92,7 +105,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here means header and library diverged
         fn.restype = res
         fn.argtypes = args
-    if lib.pmrl_abi_version() != 2:
+    if lib.pmrl_abi_version() != 3:
         raise PmrlError("libpmrl_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -124,7 +137,7 @@ def current_stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-TUNE_TILE_ROWS, TUNE_GROUP_ENVS, TUNE_CTAS_PER_SM, TUNE_FUSED, TUNE_FAST_FILL, TUNE_TMA_PIPELINE, TUNE_TMA_STAGES, TUNE_FAST_VARIANT, TUNE_RING_TMA, TUNE_TENSORMAP = 1, 2, 3, 4, 5, 8, 9, 10, 11, 12
+TUNE_GROUP_ENVS, TUNE_CTAS_PER_SM, TUNE_FUSED, TUNE_FAST_FILL, TUNE_RING_TMA = 2, 3, 4, 5, 11
 
 
 def set_tuning(key: int, value: int) -> None:

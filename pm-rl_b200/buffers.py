@@ -17,11 +17,30 @@ from . import _lib
 
 
 class DeviceRolloutBuffer:
+    """On-policy epoch buffer (replay/rollout_buffer.py:7-142) batched over E envs, in one of two storage modes:
+
+    mode="full"   s [S, E, A, W, F] is stored like the reference does (`np.zeros((E+1, A, W, F))`, :17) — 4·A·W·F bytes
+                  per env-step (13 GB per slot at 131,072 envs x 100 assets): a handful of slots fit.
+    mode="index"  per slot only the loader index bi [S, E], the raw action a [S, E, A], v, r and the un-wrapped history
+                  of post-drift weights wp [S + W - 1, E, A]; `gather` regenerates s (window by index from the device
+                  table, ring-ordered weight channel from wp) exactly like the off-policy buffer regenerates its windows
+                  (replay/buffer.py:58-77).  8·A + 12 bytes per env-step: an epoch of 1,000 steps at 65,536 envs x 100
+                  assets is 53 GB instead of 6.5 TB.  Needs the env's tables (`feat_am`, `y_tm`).
+
+    Either way the rows of a slot are written by the step kernel itself: `sinks(step)` returns the keyword arguments for
+    `BatchedTradingEnv.step_io` (reward → r[slot], action_sink → a[slot], value_sink → v[slot], obs out → s[slot + 1], …),
+    so no copy kernel runs per step.  `add` keeps the reference's call (rollout_buffer.py:43-57) for callers that have
+    the rows elsewhere."""
+
     def __init__(self, num_features: int, train_len: int, num_envs: int, num_assets: int, window_size: int,
-                 initial_cash: float = 25000.0, batch_size: int = 64, device=None, store_obs: bool = True):
+                 initial_cash: float = 25000.0, batch_size: int = 64, device=None, store_obs: bool = True,
+                 mode: str = "full", feat_am=None, y_tm=None):
         if not torch.cuda.is_available():
             raise _lib.PmrlError("DeviceRolloutBuffer needs a CUDA device (pmrl_b200 has no CPU fallback)")
+        if mode not in ("full", "index"):
+            raise ValueError("mode must be 'full' or 'index'")
         self.lib = _lib.load()
+        self.mode = mode
         self.F, self.E, self.A, self.W = num_features, num_envs, num_assets, window_size
         self.step_offset = window_size - 1                      # rollout_buffer.py:10
         self.epoch_len = train_len - self.step_offset           # rollout_buffer.py:11
@@ -31,12 +50,24 @@ class DeviceRolloutBuffer:
         dev = torch.device(device or "cuda")
         self.device = dev
         S, E, A, W, F = self.S, self.E, self.A, self.W, self.F
-        self.s = torch.zeros(S, E, A, W, F, device=dev) if store_obs else None
+        self.s = self.y = self.bi = self.wp = None
+        self.feat_am, self.y_tm = feat_am, y_tm
+        if mode == "full":
+            self.s = torch.zeros(S, E, A, W, F, device=dev) if store_obs else None
+            self.y = torch.zeros(S, E, A, device=dev)           # `prices` (rollout_buffer.py:12), filled by set_prices/add
+        else:
+            if feat_am is None or y_tm is None:
+                raise ValueError("mode='index' regenerates the windows on sample and needs feat_am [A, T, F-1] and y_tm [T, A]")
+            self.T = feat_am.shape[1]
+            self.bi = torch.zeros(S, E, dtype=torch.int32, device=dev)
+            self.wp = torch.zeros(S + W - 1, E, A, device=dev)  # wp[m] = w' after step m; wp[0] = all cash
         self.a = torch.zeros(S, E, A, device=dev)
         self.v = torch.zeros(S, E, device=dev)
         self.r = torch.zeros(S, E, device=dev)
-        self.y = torch.zeros(S, E, A, device=dev)               # `prices` (rollout_buffer.py:12), filled by set_prices/add
         self.reset()
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.s, self.y, self.bi, self.wp, self.a, self.v, self.r) if t is not None)
 
     def reset(self):
         """rollout_buffer.py:29-41 — slot 0 holds the all-cash action and the initial value."""
@@ -45,11 +76,24 @@ class DeviceRolloutBuffer:
         self.a.zero_(); self.v.zero_(); self.r.zero_()
         self.a[0, :, 0] = 1.0
         self.v[0] = self.initial_cash
+        if self.wp is not None:
+            self.wp.zero_(); self.bi.zero_()
+            self.wp[0, :, 0] = 1.0
         self.step = 1
 
     def set_prices(self, y):
         """y: price relatives per slot [S, E, A] (the reference passes train_prices[W-1:] at construction)."""
+        if self.y is None:
+            raise _lib.PmrlError("an index-mode rollout buffer reads the price relatives from y_tm")
         self.y.copy_(torch.as_tensor(y).to(self.device, torch.float32).reshape(self.S, self.E, self.A))
+
+    def fill_prices(self, env):
+        """`prices[W-1:]` of the reference constructor (rollout_buffer.py:12) for envs driven from a table: slot k holds the
+        price relatives the step of that slot saw, y_tm[t0 + k + 2(W-1)].  One-time setup gather."""
+        if self.y is None:
+            return
+        rows = env.t0.long()[None, :] + torch.arange(self.S, device=self.device)[:, None] + 2 * (self.W - 1)
+        self.y.copy_(env.y_tm[rows.clamp_(max=env.T - 1)])
 
     def slot_of(self, step=None):
         """Slot that add() will write for loader step `step` (None → the current one), or -1 while step <= W-1."""
@@ -59,10 +103,33 @@ class DeviceRolloutBuffer:
     def obs_slot(self, step=None):
         """View s[slot] ([E, A, W, F]) for the step kernel to write the observation into directly, or None."""
         k = self.slot_of(step)
-        return self.s[k] if (k >= 0 and self.s is not None) else None
+        return self.s[k] if (0 <= k < self.S and self.s is not None) else None
+
+    def sinks(self, step=None):
+        """Keyword arguments for `BatchedTradingEnv.step_io` so that the kernel stepping loader item `step` writes this
+        buffer's rows itself (then call `advance()` instead of `add()`): the obs the step RETURNS is the obs stored
+        with the next step (on_policy.py:65 stores the obs before the step), so it goes to s[slot + 1]."""
+        st = self.step if step is None else step
+        k = self.slot_of(st)
+        kw = {}
+        if 0 <= k < self.S:
+            kw.update(reward=self.r[k], action_sink=self.a[k], value_sink=self.v[k])
+            if self.bi is not None:
+                kw["index_sink"] = self.bi[k]
+        if self.wp is not None and st < self.wp.shape[0]:
+            kw["weight_sink"] = self.wp[st]
+        nxt = self.obs_slot(st + 1)
+        if nxt is not None:
+            kw["out"] = nxt
+        return kw
+
+    def advance(self):
+        self.step += 1
 
     def add(self, s, a, v, r, y=None):
         """rollout_buffer.py:43-57 batched: s [E,A,W,F] (None if already written through obs_slot), a [E,A(,1)], v [E], r [E]."""
+        if self.mode == "index":
+            raise _lib.PmrlError("an index-mode rollout buffer is filled through sinks() / step_io (it stores no observations)")
         if self.step > self.step_offset:
             slot = self.step - self.step_offset
             if slot >= self.S:
@@ -81,15 +148,34 @@ class DeviceRolloutBuffer:
                 self.y[slot].copy_(y.reshape(self.E, self.A))
         self.step += 1
 
+    def _check_slots(self, slots):
+        """slot - 1 is read (rollout_buffer.py:130-131): slots must lie in [1, S).  Checked on the host when the indices
+        are host data; device tensors are trusted (no sync on the sampling path)."""
+        if not (torch.is_tensor(slots) and slots.is_cuda):
+            arr = np.asarray(slots)
+            if arr.size and (arr.min() < 1 or arr.max() >= self.S):
+                raise IndexError(f"rollout gather: slots must be in [1, {self.S}), got [{arr.min()}, {arr.max()}]")
+
     def gather(self, slots, envs):
         """One minibatch (rollout_buffer.py:125-140): tensors shaped like the reference's
         (s [B,A,W,F], a [B,A,1], r [B,1,1], _v [B,1,1], _a [B,A,1], p [B,A,1])."""
+        self._check_slots(slots)
         slots = torch.as_tensor(slots).to(self.device, torch.int32).contiguous()
         envs = torch.as_tensor(envs).to(self.device, torch.int32).contiguous()
         B = slots.numel()
         A, W, F, dev = self.A, self.W, self.F, self.device
         s = torch.empty(B, A, W, F, device=dev); a = torch.empty(B, A, 1, device=dev); r = torch.empty(B, 1, 1, device=dev)
         pv = torch.empty(B, 1, 1, device=dev); pa = torch.empty(B, A, 1, device=dev); p = torch.empty(B, A, 1, device=dev)
+        if self.mode == "index":
+            rc = self.lib.pmrl_rollout_gather_index(self.S, self.E, A, W, F, self.T, B, _lib.ptr(slots), _lib.ptr(envs),
+                                                    _lib.ptr(self.bi), _lib.ptr(self.a), _lib.ptr(self.v), _lib.ptr(self.r),
+                                                    _lib.ptr(self.wp), _lib.ptr(self.feat_am), _lib.ptr(self.y_tm),
+                                                    _lib.ptr(s), _lib.ptr(a), _lib.ptr(r), _lib.ptr(pv), _lib.ptr(pa), _lib.ptr(p),
+                                                    _lib.current_stream())
+            _lib.check(rc, "pmrl_rollout_gather_index")
+            return s, a, r, pv, pa, p
+        if self.s is None:
+            raise _lib.PmrlError("this rollout buffer was built with store_obs=False")
         rc = self.lib.pmrl_rollout_gather(self.S, self.E, A, W, F, B, _lib.ptr(slots), _lib.ptr(envs), _lib.ptr(self.s),
                                           _lib.ptr(self.a), _lib.ptr(self.v), _lib.ptr(self.r), _lib.ptr(self.y),
                                           _lib.ptr(s), _lib.ptr(a), _lib.ptr(r), _lib.ptr(pv), _lib.ptr(pa), _lib.ptr(p),
@@ -171,6 +257,21 @@ class DeviceReplayBuffer:
         _lib.check(rc, "pmrl_replay_add")
         if not self.full and self.curr_epoch == self.max_epoch - 1:
             self.full = True
+
+    def sinks(self, e: int, step: int):
+        """Keyword arguments for `BatchedTradingEnv.step_io` so that the kernel stepping loader item `step` of epoch `e`
+        writes the (i, a, r) row itself — `i` is the env's own loader index t0 + k (buffer.py:31-37); {} for the items the
+        reference skips.  Marks the epoch like `add` does."""
+        if step < self.W - 1:
+            return {}
+        self.curr_epoch = int(e % self.max_epoch)
+        slot = step - self.step_offset
+        if slot < 0 or slot >= self.epoch_len:
+            return {}
+        if not self.full and self.curr_epoch == self.max_epoch - 1:
+            self.full = True
+        ep = self.curr_epoch
+        return dict(index_sink=self.bi[ep, slot], action_sink=self.ba[ep, slot], reward=self.br[ep, slot])
 
     def gather(self, epochs, envs, starts):
         """buffer.py:58-77 for explicit (epoch, env, start) triples → (s [B,A,W,F], a [B,A,1], r [B,1,1], s_ [B,A,W,F])."""

@@ -63,6 +63,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     srcs = _sources()
     objs = [os.path.join(OBJ_DIR, os.path.basename(s)[:-3] + ".o") for s in srcs]
+    for f in os.listdir(OBJ_DIR):                       # objects of sources that no longer exist
+        if f.endswith(".o") and os.path.join(OBJ_DIR, f) not in objs:
+            os.remove(os.path.join(OBJ_DIR, f))
     logs: list[str] = []
 
     def compile_one(pair):

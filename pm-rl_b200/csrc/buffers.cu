@@ -120,6 +120,59 @@ __global__ void __launch_bounds__(kCopyThreads) k_replay_gather(const ReplayGath
     if (p.obs_bulk_ok && tid == 0) bulk_wait_read<0>();
 }
 
+// Index-mode rollout gather: the buffer keeps (loader index, raw action, value, reward) per slot plus the un-wrapped history of
+// post-drift weights, and the observation s[slot] is REGENERATED here — feature window by index from the device table, weight
+// channel from the history with ActionBuffer.get_all's ring order (weight_buffer.py:38-39; stored slots always have a full
+// ring: slot >= 1 ↔ step n >= W) — exactly like the off-policy buffer regenerates its windows (replay/buffer.py:58-77).
+// 8·A + 12 bytes per env-step instead of 4·A·W·F.
+struct RolloutIndexGatherParams {
+    StepParams p;                 // A, W, F, T, feat_am, tile_assets, tiles_per_env, obs_bulk_ok are used
+    int S, E, B, off;             // off = W - 1: step number of a slot = slot + off (rollout_buffer.py:51-57)
+    const int32_t *slots, *envs;
+    const int32_t* bi;            // [S, E] loader item index t0 + n of the step stored in the slot
+    const float *a, *v, *r;       // [S, E, A], [S, E], [S, E]
+    const float* wp;              // [S + off, E, A] w' after step m (row 0 = all-cash)
+    const float* y_tm;            // [T, A]
+    float *s_out, *a_out, *r_out, *pv_out, *pa_out, *p_out;
+};
+__global__ void __launch_bounds__(kCopyThreads) k_rollout_gather_index(const RolloutIndexGatherParams g) {
+    extern __shared__ __align__(128) float tile[];
+    StepParams p = g.p;
+    const int b = blockIdx.x, ti = blockIdx.y;
+    const int A = p.A, W = p.W, F = p.F;
+    const int slot = g.slots[b], env = g.envs[b];
+    const int tid = threadIdx.x;
+    const size_t se = (size_t)slot * g.E + env;
+    const int i = g.bi[se];                                           // loader item of the step; the obs BEFORE it is item i - 1
+    const int t = slot + g.off - 1;                                   // steps taken when that obs was made (>= W - 1: ring full)
+    const int a0 = ti * p.tile_assets;
+    const int na = min(p.tile_assets, A - a0);
+    obs_tile_fill_features(p, tile, a0, na, i - 1, tid, kCopyThreads);
+    const int n = W * na;
+    for (int q = tid; q < n; q += kCopyThreads) {
+        const int w = q / na, al = q - w * na;                        // asset fastest → coalesced history rows
+        int d = (t - w) % W;                                          // column w shows ring slot w = newest step m <= t with m ≡ w (mod W)
+        const int m = t - d;
+        tile[(al * W + w) * F + (F - 1)] = g.wp[((size_t)m * g.E + env) * A + a0 + al];
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    p.obs = g.s_out;
+    p.obs_mode = PMRL_OBS_FULL;
+    obs_tile_store(p, tile, b, a0, na, tid, kCopyThreads);
+    if (ti == 0) {
+        const size_t sp = (size_t)(slot - 1) * g.E + env;             // idx-1 (rollout_buffer.py:130-131)
+        const float* __restrict__ yrow = g.y_tm + (size_t)(i + W - 1) * A;   // prices[idx]: the price relatives the step saw
+        for (int q = tid; q < A; q += kCopyThreads) {
+            g.a_out[(size_t)b * A + q] = g.a[se * A + q];
+            g.pa_out[(size_t)b * A + q] = g.a[sp * A + q];
+            g.p_out[(size_t)b * A + q] = yrow[q];
+        }
+        if (tid == 0) { g.r_out[b] = g.r[se]; g.pv_out[b] = g.v[sp]; }
+    }
+    if (p.obs_bulk_ok && tid == 0) bulk_wait_read<0>();
+}
+
 }  // namespace pmrl
 
 using namespace pmrl;
@@ -224,4 +277,28 @@ extern "C" int pmrl_replay_gather(int32_t P, int32_t L, int32_t E, int32_t A, in
     const size_t smem = (size_t)g.p.tile_assets * W * F * 4;
     k_replay_gather<<<dim3(B, g.p.tiles_per_env, 2), kCopyThreads, smem, (cudaStream_t)stream>>>(g);
     return pmrl_check_launch("k_replay_gather");
+}
+
+extern "C" int pmrl_rollout_gather_index(int32_t S, int32_t E, int32_t A, int32_t W, int32_t F, int32_t T, int32_t B,
+                                         const int32_t* slots, const int32_t* envs,
+                                         const int32_t* bi, const float* a, const float* v, const float* r,
+                                         const float* wp, const float* feat_am, const float* y_tm,
+                                         float* s_out, float* a_out, float* r_out, float* pv_out, float* pa_out, float* p_out,
+                                         void* stream) {
+    if (S < 2 || E < 1 || A < 1 || W < 2 || F < 2 || T < W + 1 || B < 0) return pmrl_fail(PMRL_E_SHAPE, "rollout_gather_index: bad sizes");
+    if (!slots || !envs || !bi || !a || !v || !r || !wp || !feat_am || !y_tm || !s_out || !a_out || !r_out || !pv_out || !pa_out || !p_out)
+        return pmrl_fail(PMRL_E_ARG, "rollout_gather_index: NULL pointer");
+    if ((size_t)W * F * 4 > kObsTileCapBytes) return pmrl_fail(PMRL_E_SHAPE, "rollout_gather_index: W*F*4 exceeds the tile capacity");
+    if (F - 1 == 4 && ((uintptr_t)feat_am) % 16 != 0) return pmrl_fail(PMRL_E_ALIGN, "feat_am must be 16-byte aligned");
+    if (B == 0) return 0;
+    RolloutIndexGatherParams g;
+    memset(&g, 0, sizeof(g));
+    g.p.A = A; g.p.W = W; g.p.F = F; g.p.T = T; g.p.feat_am = feat_am;
+    choose_tile(A, W, F, s_out, s_out, g.p);
+    g.S = S; g.E = E; g.B = B; g.off = W - 1;
+    g.slots = slots; g.envs = envs; g.bi = bi; g.a = a; g.v = v; g.r = r; g.wp = wp; g.y_tm = y_tm;
+    g.s_out = s_out; g.a_out = a_out; g.r_out = r_out; g.pv_out = pv_out; g.pa_out = pa_out; g.p_out = p_out;
+    const size_t smem = (size_t)g.p.tile_assets * W * F * 4;
+    k_rollout_gather_index<<<dim3(B, g.p.tiles_per_env), kCopyThreads, smem, (cudaStream_t)stream>>>(g);
+    return pmrl_check_launch("k_rollout_gather_index");
 }

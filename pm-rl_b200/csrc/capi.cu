@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <stddef.h>
 #include "pmrl_b200.h"
 #include "host_util.h"
 
@@ -38,3 +39,18 @@ int pmrl_sm_count(void) {
 extern "C" uint64_t pmrl_launch_count(void) { return (uint64_t)g_launches.load(std::memory_order_relaxed); }
 extern "C" int pmrl_abi_version(void) { return PMRL_ABI_VERSION; }
 extern "C" const char* pmrl_last_error(void) { return g_err; }
+
+// sizeof / selected field offsets of the boundary structs as compiled here (the ctypes mirror is checked against them)
+extern "C" int pmrl_abi_sizeof(int32_t which) {
+    switch (which) {
+        case 0: return (int)sizeof(PmrlEnvCfg);
+        case 1: return (int)sizeof(PmrlTables);
+        case 2: return (int)sizeof(PmrlEnvState);
+        case 3: return (int)sizeof(PmrlStepIO);
+        case 100: return (int)offsetof(PmrlStepIO, stats);
+        case 101: return (int)offsetof(PmrlStepIO, done_host);
+        case 102: return (int)offsetof(PmrlEnvState, ticket);
+        case 103: return (int)offsetof(PmrlEnvCfg, initial_cash);
+        default: return -1;
+    }
+}

@@ -5,7 +5,7 @@
 //   k_env_reset          masked re-initialisation, one env per warp.
 //   k_obs_build          one CTA per (env, asset-tile): gather window + weight channel into a shared
 //                        tile that is the byte image of obs[e, a0:a0+na, :, :], then one TMA bulk store.
-//   k_env_step_obs<NPL>  fused "Mode O": persistent CTAs, step math + obs tiles in one pass (see below).
+//   (the fused step+obs "Mode O" kernels live in env_step_rt.cu / env_step_fast.cu)
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -15,6 +15,7 @@
 #include "obs_tile.cuh"
 #include "host_util.h"
 #include "env_launch.h"
+#include <type_traits>
 
 namespace pmrl {
 
@@ -25,46 +26,127 @@ constexpr int kObsThreads = 256;
 // ------------------------------------------------------------------------------------------------
 // Mode S: state-only step.
 // ------------------------------------------------------------------------------------------------
-template <int NPL, bool HASC, bool PIPE, bool TAIL>
-__global__ void __launch_bounds__(kStepThreads) k_env_step(const StepParams p) {
+// Wide envs with commission keep w and the previous weights in registers through the mu iteration (2·NPL) and fetch the
+// price relatives after it (LOADY = false): 80 registers → three resident CTAs per SM instead of two.
+template <int NPL, bool HASC>
+constexpr bool kDeferY = HASC && (NPL == 8 || NPL == 16);
+// Resident CTAs per SM the register allocation aims for.  Narrow envs without the cross-env software pipeline (small
+// batches: one env per warp, latency-bound) want every warp of the batch resident at once — 4,096 envs are 28 warps per SM.
+template <int NPL, bool HASC, bool PIPE>
+constexpr int kStepMinBlocks = PIPE ? 2 : NPL <= 2 ? 4 : NPL == 4 ? 3 : kDeferY<NPL, HASC> ? 3 : NPL == 32 ? 1 : 2;
+
+template <int NPL, bool HASC, int VEC, bool PIPE, bool TAIL>
+__global__ void __launch_bounds__(kStepThreads, kStepMinBlocks<NPL, HASC, PIPE>) k_env_step(const StepParams p) {
     __shared__ double s_stats[kStepWarps * PMRL_STATS_LEN];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kStepWarps + warp;
     const int nw = gridDim.x * kStepWarps;
-    if (p.stats) stats_init_block(s_stats, kStepWarps);
-    double* const acc = s_stats + warp * PMRL_STATS_LEN;
+    WarpStats ws;
+    wstats_init(ws);
     StepOut so;
     if constexpr (PIPE) {
         // three envs of this warp in flight: scalars of e+2nw, vectors of e+nw, arithmetic of e
         EnvScalars s0, s1, s2;
-        EnvVectors<NPL, HASC> v0, v1;
+        EnvVectors<NPL, HASC, VEC> v0, v1;
         int e = gw;
-        if (e < p.E) { env_load_scalars(p, e, s0); env_load_vectors<NPL, HASC, TAIL>(p, e, lane, s0, v0); }
+        if (e < p.E) { env_load_scalars(p, e, s0); env_load_vectors<NPL, HASC, VEC, TAIL>(p, e, lane, s0, v0); }
         if (e + nw < p.E) env_load_scalars(p, e + nw, s1);
         for (; e < p.E; e += nw) {
             if (e + 2 * nw < p.E) env_load_scalars(p, e + 2 * nw, s2);
-            if (e + nw < p.E) env_load_vectors<NPL, HASC, TAIL>(p, e + nw, lane, s1, v1);
-            env_compute_store<NPL, HASC, TAIL>(p, e, lane, s0, v0, so, acc);
+            if (e + nw < p.E) env_load_vectors<NPL, HASC, VEC, TAIL>(p, e + nw, lane, s1, v1);
+            env_compute_store<NPL, HASC, VEC, TAIL>(p, e, lane, s0, v0, so, ws);
             s0 = s1; s1 = s2; v0 = v1;
         }
     } else {
         // wide envs (NPL >= 8): no registers for a second env's vectors.  Keep the scalars of the next two envs in
         // registers and pull the next env's DRAM rows into L2 while this one computes: the dependent chain
         // scalars → row addresses → vectors then costs one L2 hit per env instead of two DRAM round trips.
+        constexpr bool LOADY = !kDeferY<NPL, HASC>;
         EnvScalars s0, s1, s2;
         int e = gw;
         if (e < p.E) env_load_scalars(p, e, s0);
         if (e + nw < p.E) env_load_scalars(p, e + nw, s1);
         for (; e < p.E; e += nw) {
-            EnvVectors<NPL, HASC> v;
+            EnvVectors<NPL, HASC, VEC> v;
             if (e + 2 * nw < p.E) env_load_scalars(p, e + 2 * nw, s2);
-            env_load_vectors<NPL, HASC, TAIL>(p, e, lane, s0, v);
+            env_load_rows<NPL, HASC, VEC, TAIL, true, LOADY>(p, e, lane, s0, v.a, v.y, v.wl);
             if (e + nw < p.E) env_prefetch_vectors<HASC>(p, e + nw, lane, s1);
-            env_compute_store<NPL, HASC, TAIL>(p, e, lane, s0, v, so, acc);
+            env_compute_rows<NPL, HASC, VEC, TAIL, LOADY>(p, e, lane, s0, v.a, v.y, v.wl, so, ws);
             s0 = s1; s1 = s2;
         }
     }
-    if (p.stats) stats_flush_block(p.stats, s_stats, kStepWarps);
+    if (p.stats) { wstats_store(ws, s_stats + warp * PMRL_STATS_LEN, lane); stats_flush_block(p.stats, s_stats, kStepWarps); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mode S, K-step burst: ONE launch advances every env by `p.burst` steps on pre-supplied actions [K, E, A]
+// (imagination rollouts: HORIZON = 15, config/dreamer.py:54).  A warp keeps its env's V / ring pointer / local step /
+// episode return in registers across the burst and writes them back once; the weights it has just written ARE the next
+// step's previous weights (weight_buffer.py:30): the two register rows swap roles from step to step (w' of step k is
+// read as w_last by step k+1 while the dead row receives the next action), so per step only the action row comes from
+// DRAM — requested one step ahead (into registers for narrow envs, into L2 for wide ones).  Reward / done / the ring row
+// are written every step; a burst is bit-identical to K eager steps.
+// ------------------------------------------------------------------------------------------------
+template <int NPL, bool HASC, int VEC, bool TAIL>
+__global__ void __launch_bounds__(kStepThreads, kStepMinBlocks<NPL, HASC, false>) k_env_step_burst(const StepParams p) {
+    __shared__ double s_stats[kStepWarps * PMRL_STATS_LEN];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * kStepWarps + warp;
+    const int nw = gridDim.x * kStepWarps;
+    WarpStats ws;
+    wstats_init(ws);
+    const int K = p.burst;
+    const size_t EA = (size_t)p.E * p.A;
+    constexpr bool REGPF = (NPL <= 4);                   // next step's action / y rows prefetched into registers
+    constexpr bool LOADY = !kDeferY<NPL, HASC>;
+    constexpr int WLN = HASC ? NPL : 1;
+    for (int e = gw; e < p.E; e += nw) {
+        StepParams q = p;                                 // per-step views: actions[k], reward[k], done[k]
+        EnvScalars sc;
+        env_load_scalars(p, e, sc);
+        float X[NPL], Y[WLN], yv[NPL];                    // X / Y: (action → w', previous weights), roles swap every step (HASC)
+        float an[REGPF ? NPL : 1], yn[REGPF ? NPL : 1];
+        StepOut so;
+        env_load_rows<NPL, HASC, VEC, TAIL, true, LOADY>(q, e, lane, sc, X, yv, Y);
+        // one step: `a` holds the action (step 0 / narrow envs) or receives it here (wide envs, k > 0); `wl` = previous weights
+        auto step = [&](float (&a)[NPL], float (&wl)[WLN], float (&nxt)[HASC ? NPL : NPL], int k) {
+            EnvScalars sn = sc;                           // the local step after this one is known before the arithmetic,
+            sn.k = env_needs_reset(p, sc) ? 0 : sc.k + 1; // so the next step's rows are requested now
+            if (k + 1 < K) {
+                StepParams qn = q;
+                qn.actions = q.actions + EA;
+                float none[1];
+                if constexpr (REGPF) env_load_rows<NPL, false, VEC, TAIL, false, true>(qn, e, lane, sn, an, yn, none);
+                else env_prefetch_vectors<false>(qn, e, lane, sn);
+            }
+            if constexpr (!REGPF) {
+                if (k > 0) { float none[1]; env_load_rows<NPL, false, VEC, TAIL, false, LOADY>(q, e, lane, sc, a, yv, none); }
+            }
+            env_compute_rows<NPL, HASC, VEC, TAIL, LOADY, false>(q, e, lane, sc, a, yv, wl, so, ws);
+            sc.V = so.V; sc.i = so.idx_new; sc.full = so.is_full; sc.k = so.k; sc.epr = so.epr;
+            q.actions += EA; q.reward += p.E; q.done += p.E;
+            if (q.reward_host) { q.reward_host += p.E; q.done_host += p.E; }
+            if constexpr (REGPF) {                        // narrow envs: the prefetched rows move into the row that is now dead
+                if (k + 1 < K) {
+#pragma unroll
+                    for (int j = 0; j < NPL; ++j) { nxt[j] = an[j]; yv[j] = yn[j]; }
+                }
+            }
+        };
+        if constexpr (HASC) {
+            for (int k = 0; k < K; k += 2) {
+                step(X, Y, Y, k);                         // w' → X; next action → Y
+                if (k + 1 < K) step(Y, X, X, k + 1);      // w' → Y; next action → X
+            }
+        } else {
+            for (int k = 0; k < K; ++k) step(X, Y, X, k);
+        }
+        if (lane == 0) {                                  // the scalar state goes back once per burst
+            p.value[e] = sc.V; p.idx[e] = sc.i; p.is_full[e] = (uint8_t)sc.full; p.t[e] = sc.k;
+            if (p.ep_return) p.ep_return[e] = sc.epr;
+        }
+    }
+    if (p.stats) { wstats_store(ws, s_stats + warp * PMRL_STATS_LEN, lane); stats_flush_block(p.stats, s_stats, kStepWarps); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -173,152 +255,12 @@ __global__ void __launch_bounds__(kObsThreads) k_obs_build_rows(const StepParams
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Mode O, fused: step + observation in one pass.
-//
-// A CTA owns a *group* of G consecutive envs at a time (persistent, grid-stride over groups):
-//   phase 1  warp w advances env e0+w (env_step_warp) and leaves w', the new ring pointer and the
-//            window row in shared memory;
-//   phase 2  all warps stream the group's observations.  The obs of G consecutive envs is one
-//            contiguous [G*A, W, F] slab, so tiles are TA asset-rows cut across env boundaries (no
-//            ragged per-env tiles); each tile is assembled in one of two shared buffers and leaves
-//            as a single TMA bulk store while the next tile is being filled.
-// The row written by this step comes from shared memory (never re-read from global), so the ring is
-// read exactly once and written exactly once per step: 4·W + 4 bytes per asset-step of ring traffic.
-// ------------------------------------------------------------------------------------------------
-constexpr int kFusedThreads = 256;
-constexpr int kFusedWarps = kFusedThreads / 32;
-constexpr int kMaxGroup = kFusedWarps;
-
-struct GroupEnv { int row0, shift, fresh_slot, pad; };   // per env of the group (phase 1 → phase 2)
-
-template <int NPL, bool HASC, int MINB>
-__global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs(const StepParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ double s_stats[kFusedWarps * PMRL_STATS_LEN];
-    __shared__ GroupEnv s_env[kMaxGroup];
-    const int A = p.A, W = p.W, F = p.F, T = p.T, TA = p.tile_assets, G = p.group_envs;
-    const int tile_floats = TA * W * F;
-    float* const tile0 = reinterpret_cast<float*>(smem_raw);
-    float* const tile1 = tile0 + tile_floats;
-    float* const s_wnew = tile1 + tile_floats;           // [G, A]   w' of the group's envs, indexed by asset-row
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_groups = (p.E + G - 1) / G;
-    const size_t row_floats = (size_t)W * F;
-    if (p.stats) stats_init_block(s_stats, kFusedWarps);
-    const uint64_t pol_keep = kPolicyEvictLast, pol_once = kPolicyEvictFirst;
-    int buf = 0;
-    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int e0 = grp * G;
-        const int ne = min(G, p.E - e0);
-        // ---------------- phase 1: one warp per env ----------------
-        if (warp < ne) {
-            const int e = e0 + warp;
-            EnvVectors<NPL, HASC> ev;
-            StepOut so;
-            env_step_warp<NPL, HASC>(p, e, lane, ev, so, s_stats + warp * PMRL_STATS_LEN);
-#pragma unroll
-            for (int j = 0; j < NPL; ++j) {
-                const int a = lane + 32 * j;
-                if (a < A) s_wnew[warp * A + a] = ev.a[j];
-            }
-            if (lane == 0) {
-                GroupEnv ge;
-                ge.row0 = p.t0[e] + so.k;
-                ge.shift = so.is_full ? 0 : (W - so.idx_new);            // weight_buffer.py:38-42
-                ge.fresh_slot = so.did_reset ? 0 : so.slot_written;       // rows written by this launch come from smem
-                ge.pad = 0;
-                s_env[warp] = ge;
-            }
-        }
-        __syncthreads();
-        // ---------------- phase 2: tiles over the group's [ne*A] asset-rows ----------------
-        const int R = ne * A;
-        const int ntiles = (R + TA - 1) / TA;
-        float* const obs_grp = p.obs + (size_t)e0 * A * row_floats;
-
-        for (int ti = 0; ti < ntiles; ++ti) {
-            float* const tile = buf ? tile1 : tile0;
-            if (tid == 0) bulk_wait_read<1>();            // the store that last used this buffer has drained
-            __syncthreads();
-            const int r0 = ti * TA;
-            const int nr = min(TA, R - r0);
-            // -- feature channels: one warp per asset-row, lanes over the window rows --
-            if (F - 1 == 4) {
-                const float4* __restrict__ tbl = reinterpret_cast<const float4*>(p.feat_am);
-                for (int ar = warp; ar < nr; ar += kFusedWarps) {
-                    const int gar = r0 + ar;
-                    const int el = gar / A, a = gar - el * A;
-                    const float4* __restrict__ src = tbl + (size_t)a * T + s_env[el].row0;
-                    float* __restrict__ dst = tile + (size_t)ar * W * 5;
-                    for (int w = lane; w < W; w += 32) {
-                        const float4 v = ld_keep4(src + w, pol_keep);
-                        float* d = dst + w * 5;
-                        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-                    }
-                }
-            } else {
-                const int Fm1 = F - 1, per = W * Fm1;
-                for (int ar = warp; ar < nr; ar += kFusedWarps) {
-                    const int gar = r0 + ar;
-                    const int el = gar / A, a = gar - el * A;
-                    const float* __restrict__ src = p.feat_am + ((size_t)a * T + s_env[el].row0) * Fm1;
-                    float* __restrict__ dst = tile + (size_t)ar * W * F;
-                    for (int q = lane; q < per; q += 32) {
-                        const int w = q / Fm1, c = q - w * Fm1;
-                        dst[w * F + c] = ld_keep(src + q, pol_keep);
-                    }
-                }
-            }
-            // -- weight channel: lane = asset-row (coalesced ring rows), warps over the window columns --
-            for (int ar = lane; ar < nr; ar += 32) {
-                const int gar = r0 + ar;
-                const int el = gar / A, a = gar - el * A;
-                const GroupEnv ge = s_env[el];
-                const float* __restrict__ hist_ea = p.hist + ((size_t)(e0 + el) * W) * A + a;
-                const float fresh = s_wnew[el * A + a];
-                float* __restrict__ dst = tile + (size_t)ar * W * F + (F - 1);
-#pragma unroll 4
-                for (int w = warp; w < W; w += kFusedWarps) {
-                    const int slot = w - ge.shift;
-                    float v = 0.0f;
-                    if (slot >= 0) v = (slot == ge.fresh_slot) ? fresh : ld_once(hist_ea + (size_t)slot * A, pol_once);
-                    dst[w * F] = v;
-                }
-            }
-            fence_proxy_async_smem();
-            __syncthreads();
-            // -- tile → global --
-            float* const gdst = obs_grp + (size_t)r0 * row_floats;
-            const int n = nr * W * F;
-            if (((((uintptr_t)gdst) | ((size_t)n * 4)) & 15) == 0) {
-                if (tid == 0) { bulk_store_s2g(gdst, tile, (uint32_t)n * 4u, pol_once); bulk_commit(); }
-            } else {
-                for (int q = tid; q < n; q += kFusedThreads) gdst[q] = tile[q];
-            }
-            buf ^= 1;
-        }
-    }
-    if (tid == 0) bulk_wait_read<0>();
-    if (p.stats) stats_flush_block(p.stats, s_stats, kFusedWarps);
-}
-
 }  // namespace pmrl
 
 // ================================================================================================
 // Host side: validation, tiling choice, launches.
 // ================================================================================================
 using namespace pmrl;
-
-static int npl_for(int A) {
-    if (A <= 32) return 1;
-    if (A <= 64) return 2;
-    if (A <= 128) return 4;
-    if (A <= 256) return 8;
-    if (A <= 512) return 16;
-    if (A <= 1024) return 32;
-    return 0;
-}
 
 // Pick the asset-tile of the obs kernels: the biggest tile ≤ cap bytes whose start offsets stay
 // 16-byte aligned (so the TMA bulk store applies) with the least ragged last tile.
@@ -362,6 +304,7 @@ static int fill_params(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlE
     if (tbl) { p.y_tm = tbl->y_tm; p.feat_am = tbl->feat_am; }
     p.value = st->value; p.hist = st->hist; p.idx = st->idx; p.is_full = st->is_full; p.t = st->t;
     p.t0 = st->t0; p.sharpe = st->sharpe; p.ep_return = st->ep_return;
+    p.ticket = st->ticket;
     return 0;
 }
 
@@ -373,15 +316,18 @@ static int check_obs_args(const StepParams& p, const float* obs, int obs_mode) {
     if (p.F < 2 && obs_mode == PMRL_OBS_FULL) return pmrl_fail(PMRL_E_SHAPE, "F >= 2 required for a full obs");
     if (obs_mode == PMRL_OBS_FULL) {
         if (!p.feat_am) return pmrl_fail(PMRL_E_ARG, "feat_am is NULL but obs_mode == FULL");
+        if (!p.t0) return pmrl_fail(PMRL_E_ARG, "t0 is NULL but obs_mode == FULL");
         if (p.F - 1 == 4 && ((uintptr_t)p.feat_am) % 16 != 0) return pmrl_fail(PMRL_E_ALIGN, "feat_am must be 16-byte aligned");
         if (p.T < p.W) return pmrl_fail(PMRL_E_SHAPE, "T < W");
+        // the window rows are [t0 + k, t0 + k + W): without an episode length k grows without bound and would leave the table
+        if (p.episode_len <= 0) return pmrl_fail(PMRL_E_SHAPE, "obs_mode FULL gathers from the feature table and needs episode_len > 0");
     }
     if ((size_t)p.W * p.F * 4 > kObsTileCapBytes) return pmrl_fail(PMRL_E_SHAPE, "W*F*4 exceeds the obs tile capacity");
     return 0;
 }
 
 // Launch-shape knobs (pmrl_set_tuning).
-static int g_tune_rows = 0, g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1, g_tune_fast = 1, g_tune_tma = 0, g_tune_stages = 0, g_tune_rt = 1, g_tune_tm = 0;
+static int g_tune_group = 0, g_tune_ctas_per_sm = 0, g_tune_fused = 1, g_tune_fast = 1, g_tune_rt = 1;
 
 static int launch_obs(StepParams& p, float* obs, int obs_mode, cudaStream_t s) {
     p.obs = obs; p.obs_mode = obs_mode;
@@ -403,110 +349,80 @@ static int launch_obs(StepParams& p, float* obs, int obs_mode, cudaStream_t s) {
     return pmrl_check_launch("k_obs_build");
 }
 
-template <int NPL, bool HASC>
-static int launch_step_s(const StepParams& p, cudaStream_t s) {
-    constexpr bool PIPE = (NPL <= 4);                 // 3-stage software pipeline while the registers allow it
+// (NPL, VEC) dispatch shared by the eager and the burst launchers: F is a generic lambda called with
+// std::integral_constant<int, NPL>, <int, VEC>.
+template <typename Fn>
+static int dispatch_npl_vec(int npl, int vec, Fn&& f) {
+#define PMRL_NV(N, V) if (npl == N && vec == V) return f(std::integral_constant<int, N>{}, std::integral_constant<int, V>{})
+    PMRL_NV(1, 1); PMRL_NV(2, 1); PMRL_NV(2, 2); PMRL_NV(4, 1); PMRL_NV(4, 2); PMRL_NV(4, 4);
+    PMRL_NV(8, 1); PMRL_NV(8, 4); PMRL_NV(16, 1); PMRL_NV(16, 4); PMRL_NV(32, 1); PMRL_NV(32, 4);
+#undef PMRL_NV
+    return pmrl_fail(PMRL_E_SHAPE, "unsupported (slots per lane, vector width)");
+}
+
+static int launch_step_s(const StepParams& p, int npl, int vec, cudaStream_t s) {
     const int want = (p.E + kStepWarps - 1) / kStepWarps;
     const int cap = pmrl_sm_count() * 8;
-    // TAIL: every 32-asset slot row but the last is full → only the last row carries validity guards
-    if (p.A > 32 * (NPL - 1)) k_env_step<NPL, HASC, PIPE, true><<<want < cap ? want : cap, kStepThreads, 0, s>>>(p);
-    else k_env_step<NPL, HASC, PIPE, false><<<want < cap ? want : cap, kStepThreads, 0, s>>>(p);
-    return pmrl_check_launch("k_env_step");
+    const int grid = want < cap ? want : cap;
+    const bool hasc = p.commission > 0.0f;
+    return dispatch_npl_vec(npl, vec, [&](auto N, auto V) {
+        constexpr int NPL = decltype(N)::value, VEC = decltype(V)::value;
+        // TAIL: every group of 32·VEC asset slots but the last is full → only the last group carries validity guards
+        const bool tail = env_tail_ok<NPL, VEC>(p.A);
+        auto go = [&](auto H, auto P, auto T) {
+            k_env_step<NPL, decltype(H)::value, VEC, decltype(P)::value, decltype(T)::value><<<grid, kStepThreads, 0, s>>>(p);
+            return pmrl_check_launch("k_env_step");
+        };
+        using Tr = std::true_type; using Fa = std::false_type;
+        // 3-stage software pipeline over the envs of a warp while the registers allow it (narrow envs) and a warp has more
+        // than one env; a batch that fits one wave runs the plain form at full occupancy
+        if constexpr (NPL <= 4) {
+            if (want > cap) {
+                if (hasc) return tail ? go(Tr{}, Tr{}, Tr{}) : go(Tr{}, Tr{}, Fa{});
+                return tail ? go(Fa{}, Tr{}, Tr{}) : go(Fa{}, Tr{}, Fa{});
+            }
+        }
+        if (hasc) return tail ? go(Tr{}, Fa{}, Tr{}) : go(Tr{}, Fa{}, Fa{});
+        return tail ? go(Fa{}, Fa{}, Tr{}) : go(Fa{}, Fa{}, Fa{});
+    });
 }
 
-template <bool HASC>
-static int launch_step_npl(const StepParams& p, int npl, cudaStream_t s) {
-    switch (npl) {
-        case 1: return launch_step_s<1, HASC>(p, s);
-        case 2: return launch_step_s<2, HASC>(p, s);
-        case 4: return launch_step_s<4, HASC>(p, s);
-        case 8: return launch_step_s<8, HASC>(p, s);
-        case 16: return launch_step_s<16, HASC>(p, s);
-        default: return launch_step_s<32, HASC>(p, s);
-    }
+static int launch_step_burst(const StepParams& p, int npl, int vec, cudaStream_t s) {
+    const int want = (p.E + kStepWarps - 1) / kStepWarps;
+    const int cap = pmrl_sm_count() * 8;
+    const int grid = want < cap ? want : cap;
+    const bool hasc = p.commission > 0.0f;
+    return dispatch_npl_vec(npl, vec, [&](auto N, auto V) {
+        constexpr int NPL = decltype(N)::value, VEC = decltype(V)::value;
+        const bool tail = env_tail_ok<NPL, VEC>(p.A);
+        if (hasc) { if (tail) k_env_step_burst<NPL, true, VEC, true><<<grid, kStepThreads, 0, s>>>(p); else k_env_step_burst<NPL, true, VEC, false><<<grid, kStepThreads, 0, s>>>(p); }
+        else      { if (tail) k_env_step_burst<NPL, false, VEC, true><<<grid, kStepThreads, 0, s>>>(p); else k_env_step_burst<NPL, false, VEC, false><<<grid, kStepThreads, 0, s>>>(p); }
+        return pmrl_check_launch("k_env_step_burst");
+    });
 }
-
 
 extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
     switch (key) {
-        case PMRL_TUNE_TILE_ROWS: g_tune_rows = value; return 0;
         case PMRL_TUNE_GROUP_ENVS: g_tune_group = value; return 0;
         case PMRL_TUNE_CTAS_PER_SM: g_tune_ctas_per_sm = value; return 0;
         case PMRL_TUNE_FUSED: g_tune_fused = value; return 0;
         case PMRL_TUNE_FAST_FILL: g_tune_fast = value; return 0;
-        case PMRL_TUNE_TMA_PIPELINE: g_tune_tma = value; return 0;
-        case PMRL_TUNE_TMA_STAGES: g_tune_stages = value; return 0;
-        case PMRL_TUNE_FAST_VARIANT: pmrl_set_fast_variant(value); return 0;
         case PMRL_TUNE_RING_TMA: g_tune_rt = value; return 0;
-        case PMRL_TUNE_TENSORMAP: g_tune_tm = value; return 0;
         default: return pmrl_fail(PMRL_E_ARG, "unknown tuning key");
     }
 }
 
-template <int NPL, bool HASC, int MINB>
-static int launch_fused_t(StepParams& p, size_t smem, int grid, cudaStream_t s) {
-    static bool attr_done[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs<NPL, HASC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return pmrl_fail((int)e, "cudaFuncSetAttribute(k_env_step_obs) failed");
-        attr_done[dev] = true;
-    }
-    k_env_step_obs<NPL, HASC, MINB><<<grid, kFusedThreads, smem, s>>>(p);
-    return pmrl_check_launch("k_env_step_obs");
-}
-
-template <bool HASC>
-static int launch_fused_npl(StepParams& p, size_t smem, int grid, int npl, cudaStream_t s) {
-    switch (npl) {
-        case 1: return launch_fused_t<1, HASC, 3>(p, smem, grid, s);
-        case 2: return launch_fused_t<2, HASC, 3>(p, smem, grid, s);
-        case 4: return launch_fused_t<4, HASC, 3>(p, smem, grid, s);
-        case 8: return launch_fused_t<8, HASC, 2>(p, smem, grid, s);
-        case 16: return launch_fused_t<16, HASC, 1>(p, smem, grid, s);
-        default: return launch_fused_t<32, HASC, 1>(p, smem, grid, s);
-    }
-}
-
-static int launch_fused(StepParams& p, float* obs, int npl, cudaStream_t s) {
+static int launch_fused(StepParams& p, float* obs, int npl, int vec, cudaStream_t s) {
     p.obs = obs; p.obs_mode = PMRL_OBS_FULL;
-    if (g_tune_fast && g_tune_tma) {                  // warp-specialised TMA pipeline (env_step_tma.cu)
-        const int rc = pmrl_launch_step_obs_tma(p, npl, g_tune_stages, g_tune_group, s);
-        if (rc != -100) return rc;                    // -100: shape not covered by that variant → fall through
-    }
-    if (g_tune_fast && g_tune_tm) {                   // all loads through TMA: tensor-map feature boxes + ring bulk loads (env_step_tm.cu)
-        const int rc = pmrl_launch_step_obs_tm(p, npl, g_tune_group, g_tune_ctas_per_sm, s);
+    if (!g_tune_fast) return -100;
+    if (g_tune_rt) {                                  // ring rows through one TMA bulk load per env (env_step_rt.cu)
+        p.prefetch_next = (g_tune_rt == 2) ? 0 : 1;
+        const int rc = pmrl_launch_step_obs_rt(p, npl, vec, g_tune_group, g_tune_ctas_per_sm, s);
         if (rc != -100) return rc;
     }
-    if (g_tune_fast && g_tune_rt) {                   // ring rows through one TMA bulk load per env (env_step_rt.cu)
-        p.tma_stages = (g_tune_rt == 2) ? 0 : 1;      // RT reuses this field: 1 = prefetch the next group's phase-1 inputs into L2
-        const int rc = pmrl_launch_step_obs_rt(p, npl, g_tune_group, g_tune_ctas_per_sm, s);
-        if (rc != -100) return rc;
-    }
-    if (g_tune_fast && (g_tune_rows <= 0 || g_tune_rows == 32)) {   // register-staged fill (env_step_fast.cu): F == 5, W <= 64, A <= 128
-        const int rc = pmrl_launch_step_obs_fast(p, npl, g_tune_group, g_tune_ctas_per_sm, s);
-        if (rc != -100) return rc;
-    }
-    // No specialised kernel covers this shape.  The generic fused kernel below loses to the two-kernel path (state-only
-    // step, then k_obs_build) on every shape measured — 32,768 x 500 x 50: 20.9 ms vs 4.5 ms; 131,072 x 100 x 50 with the
-    // specialised kernels disabled: 6.9 ms vs 3.8 ms — so it only runs when asked for (PMRL_TUNE_FUSED = 2).
-    if (g_tune_fused != 2) return -100;
-    const size_t row_bytes = (size_t)p.W * p.F * 4;
-    int rows = g_tune_rows > 0 ? g_tune_rows : 32;
-    while (rows > 1 && rows * row_bytes > 36 * 1024) rows >>= 1;
-    p.tile_assets = rows;
-    int ctas_per_sm = g_tune_ctas_per_sm > 0 ? g_tune_ctas_per_sm : (npl <= 4 ? 3 : (npl <= 8 ? 2 : 1));
-    const int slots = pmrl_sm_count() * ctas_per_sm;
-    int G = g_tune_group > 0 ? g_tune_group : kMaxGroup;
-    if (G > kMaxGroup) G = kMaxGroup;
-    while (G > 1 && (p.E + G - 1) / G < 2 * slots) G >>= 1;     // small batches: more, smaller groups
-    p.group_envs = G;
-    const size_t smem = 2 * rows * row_bytes + (size_t)G * p.A * 4;
-    if (smem > 200 * 1024) return pmrl_fail(PMRL_E_SHAPE, "fused step: shared-memory budget exceeded");
-    const int n_groups = (p.E + G - 1) / G;
-    const int grid = n_groups < slots ? n_groups : slots;
-    return p.commission > 0.0f ? launch_fused_npl<true>(p, smem, grid, npl, s) : launch_fused_npl<false>(p, smem, grid, npl, s);
+    // register-staged fill (env_step_fast.cu): F == 5, W <= 64, A <= 128 — the shapes RT's ring alignment excludes
+    return pmrl_launch_step_obs_fast(p, npl, vec, g_tune_group, g_tune_ctas_per_sm, s);
+    // -100: no fused kernel covers this shape (A > 128, F != 5, W > 64) → state-only step, then the obs tile kernel
 }
 
 extern "C" int pmrl_env_reset(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
@@ -515,10 +431,8 @@ extern "C" int pmrl_env_reset(const PmrlEnvCfg* cfg, const PmrlTables* tbl, cons
     StepParams p;
     if (int rc = fill_params(cfg, tbl, st, p)) return rc;
     if (int rc = check_obs_args(p, obs, obs_mode)) return rc;
-    if (obs_mode == PMRL_OBS_FULL && !p.t0) return pmrl_fail(PMRL_E_ARG, "t0 is NULL but obs_mode == FULL");
     p.mask = mask;
     cudaStream_t s = (cudaStream_t)stream;
-    if (p.E == 0) return 0;
     const int want = (p.E + kStepWarps - 1) / kStepWarps;
     const int cap = pmrl_sm_count() * 8;
     k_env_reset<<<want < cap ? want : cap, kStepThreads, 0, s>>>(p);
@@ -546,6 +460,7 @@ extern "C" int pmrl_price_relatives(const float* close_tm, int32_t T, int32_t A,
 
 // Bit-for-bit comparison of the shared-reciprocal quotient (pmrl_device.cuh: unidiv) with IEEE division on caller-supplied
 // operands: den[i / 32] divides num[i]; pairs outside the range the kernels accept are skipped and counted separately.
+// Even i take the scalar form, odd i the packed (FMUL2 / FFMA2) form the step kernels use.
 __global__ void k_selftest_division(const float* __restrict__ num, const float* __restrict__ den, long long n,
                                     unsigned long long* __restrict__ out /* [2]: mismatches, pairs tested */) {
     unsigned long long bad = 0, tested = 0;
@@ -553,7 +468,10 @@ __global__ void k_selftest_division(const float* __restrict__ num, const float* 
         const float a = num[i], b = den[i >> 5];
         if (!unidiv_in_range(b) || !(a == 0.0f || unidiv_in_range(a))) continue;
         const UniDiv d = unidiv_make(b);
-        const float q = unidiv(a, d), ref = __fdiv_rn(a, b);
+        float q;
+        if (i & 1) { float x[2] = {a, a}; lane_unidiv(x, d); q = x[1]; }
+        else q = unidiv(a, d);
+        const float ref = __fdiv_rn(a, b);
         ++tested;
         if (__float_as_uint(q) != __float_as_uint(ref)) ++bad;
     }
@@ -576,39 +494,81 @@ extern "C" int pmrl_obs_build(const PmrlEnvCfg* cfg, const PmrlTables* tbl, cons
     if (int rc = fill_params(cfg, tbl, st, p)) return rc;
     if (obs_mode == PMRL_OBS_NONE) return pmrl_fail(PMRL_E_ARG, "obs_mode NONE makes no obs");
     if (int rc = check_obs_args(p, obs, obs_mode)) return rc;
-    if (obs_mode == PMRL_OBS_FULL && !p.t0) return pmrl_fail(PMRL_E_ARG, "t0 is NULL but obs_mode == FULL");
     return launch_obs(p, obs, obs_mode, (cudaStream_t)stream);
 }
 
-extern "C" int pmrl_env_step(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
-                             const float* actions, const float* y_ext,
-                             float* reward, uint8_t* done, float* obs, int32_t obs_mode,
-                             double* stats, void* stream) {
-    if (cfg && cfg->E == 0) return 0;                  // empty batch: nothing to do (state pointers may be NULL)
-    StepParams p;
+// validation shared by the step entry points; fills the per-step fields of p
+static int prepare_step(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st, const PmrlStepIO* io, StepParams& p) {
     if (int rc = fill_params(cfg, tbl, st, p)) return rc;
-    if (!actions || !reward || !done) return pmrl_fail(PMRL_E_ARG, "actions/reward/done is NULL");
-    if (!y_ext) {
+    if (!io) return pmrl_fail(PMRL_E_ARG, "io is NULL");
+    if (!io->actions || !io->reward || !io->done) return pmrl_fail(PMRL_E_ARG, "actions/reward/done is NULL");
+    if (!io->y_ext) {
         if (!p.y_tm) return pmrl_fail(PMRL_E_ARG, "need y_tm (pmrl_price_relatives) or y_ext");
         if (!p.t0) return pmrl_fail(PMRL_E_ARG, "t0 is NULL but y comes from the price table");
         if (p.episode_len <= 0) return pmrl_fail(PMRL_E_SHAPE, "episode_len must be > 0 when y comes from the price table");
     }
     if (cfg->reward_mode < 0 || cfg->reward_mode > PMRL_REWARD_SHARPE) return pmrl_fail(PMRL_E_ARG, "bad reward_mode");
     if (cfg->reward_mode == PMRL_REWARD_SHARPE && !p.sharpe) return pmrl_fail(PMRL_E_ARG, "sharpe state is NULL");
-    if (stats && !p.ep_return) return pmrl_fail(PMRL_E_ARG, "ep_return is NULL but stats requested");
+    if (io->stats && !p.ep_return) return pmrl_fail(PMRL_E_ARG, "ep_return is NULL but stats requested");
+    if ((io->reward_host == nullptr) != (io->done_host == nullptr)) return pmrl_fail(PMRL_E_ARG, "reward_host and done_host go together");
+    if (io->index_sink && !p.t0) return pmrl_fail(PMRL_E_ARG, "index_sink needs t0");
+    if (!env_npl_for(p.A)) return pmrl_fail(PMRL_E_SHAPE, "A > 1024 is not supported");
+    p.actions = io->actions; p.y_ext = io->y_ext; p.reward = io->reward; p.done = io->done; p.stats = io->stats;
+    p.action_sink = io->action_sink; p.value_sink = io->value_sink; p.index_sink = io->index_sink; p.weight_sink = io->weight_sink;
+    p.reward_host = io->reward_host; p.done_host = io->done_host;
+    return 0;
+}
+
+// 16-byte (VEC = 4) / 8-byte (VEC = 2) row accesses need every row base aligned: rows start at multiples of A floats
+// from these bases, and A % VEC == 0 whenever VEC > 1.
+static int vec_for_pointers(const StepParams& p, int npl) {
+    int vec = env_vec_for(p.A, npl);
+    uintptr_t m = (uintptr_t)p.actions | (uintptr_t)p.hist | (uintptr_t)p.action_sink | (uintptr_t)p.weight_sink;
+    m |= p.y_ext ? (uintptr_t)p.y_ext : (uintptr_t)p.y_tm;
+    while (vec > 1 && (m % (4u * vec)) != 0) vec = (vec == 4 && npl < 8 && p.A % 2 == 0) ? 2 : 1;
+    return vec;
+}
+
+extern "C" int pmrl_env_step_io(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
+                                const PmrlStepIO* io, void* stream) {
+    if (cfg && cfg->E == 0) return 0;                  // empty batch: nothing to do (state pointers may be NULL)
+    StepParams p;
+    if (int rc = prepare_step(cfg, tbl, st, io, p)) return rc;
+    float* obs = io->obs;
+    const int obs_mode = io->obs_mode;
     if (int rc = check_obs_args(p, obs, obs_mode)) return rc;
-    if (obs_mode == PMRL_OBS_FULL && !p.t0) return pmrl_fail(PMRL_E_ARG, "t0 is NULL but obs_mode == FULL");
-    const int npl = npl_for(p.A);
-    if (!npl) return pmrl_fail(PMRL_E_SHAPE, "A > 1024 is not supported");
-    p.actions = actions; p.y_ext = y_ext; p.reward = reward; p.done = done; p.stats = stats;
+    const int npl = env_npl_for(p.A), vec = vec_for_pointers(p, npl);
     cudaStream_t s = (cudaStream_t)stream;
-    if (p.E == 0) return 0;
     if (obs_mode == PMRL_OBS_FULL && g_tune_fused && (size_t)p.W * p.F * 4 <= 36 * 1024) {
-        const int rc = launch_fused(p, obs, npl, s);
+        const int rc = launch_fused(p, obs, npl, vec, s);
         if (rc != -100) return rc;                    // -100: no fused kernel for this shape → step kernel + obs kernel
     }
-    int rc = p.commission > 0.0f ? launch_step_npl<true>(p, npl, s) : launch_step_npl<false>(p, npl, s);
-    if (rc) return rc;
+    if (int rc = launch_step_s(p, npl, vec, s)) return rc;
     if (obs_mode != PMRL_OBS_NONE) return launch_obs(p, obs, obs_mode, s);
     return 0;
+}
+
+extern "C" int pmrl_env_step(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
+                             const float* actions, const float* y_ext,
+                             float* reward, uint8_t* done, float* obs, int32_t obs_mode,
+                             double* stats, void* stream) {
+    PmrlStepIO io;
+    memset(&io, 0, sizeof(io));
+    io.actions = actions; io.y_ext = y_ext; io.reward = reward; io.done = done; io.obs = obs; io.obs_mode = obs_mode; io.stats = stats;
+    return pmrl_env_step_io(cfg, tbl, st, &io, stream);
+}
+
+extern "C" int pmrl_env_step_burst(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
+                                   const float* actions, int32_t K, float* reward, uint8_t* done,
+                                   double* stats, void* stream) {
+    if (cfg && cfg->E == 0) return 0;
+    if (K < 1) return pmrl_fail(PMRL_E_SHAPE, "env_step_burst: K >= 1 required");
+    PmrlStepIO io;
+    memset(&io, 0, sizeof(io));
+    io.actions = actions; io.reward = reward; io.done = done; io.stats = stats;
+    StepParams p;
+    if (int rc = prepare_step(cfg, tbl, st, &io, p)) return rc;
+    p.burst = K;
+    const int npl = env_npl_for(p.A), vec = vec_for_pointers(p, npl);
+    return launch_step_burst(p, npl, vec, (cudaStream_t)stream);
 }

@@ -41,7 +41,7 @@ struct GroupEnv { int row0, shift, fresh_slot, pad; };   // per env of the group
 struct FeatRegs { float4 fv[4][2]; };     // one tile of in-flight table loads of a thread
 struct RingRegs { float wv[8]; float fresh; int shift, wf; };   // one tile of in-flight ring loads of a thread
 
-template <int NPL, bool HASC, int WT, bool RING2, int MINB>
+template <int NPL, bool HASC, int VEC, int WT, bool RING2, int MINB>
 __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs_fast(const StepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_stats[kFusedWarps * PMRL_STATS_LEN];
@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs_fast(const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_groups = (p.E + G - 1) / G;
     const size_t row_floats = (size_t)W * 5;
-    if (p.stats) stats_init_block(s_stats, kFusedWarps);
+    WarpStats ws;
+    wstats_init(ws);
     const uint64_t pol_keep = kPolicyEvictLast, pol_once = kPolicyEvictFirst;   // immediates: no per-load register moves
     int buf = 0;
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
@@ -65,12 +66,12 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs_fast(const
         // ---------------- phase 1: one warp per env ----------------
         if (warp < ne) {
             const int e = e0 + warp;
-            EnvVectors<NPL, HASC> ev;
+            EnvVectors<NPL, HASC, VEC> ev;
             StepOut so;
-            env_step_warp<NPL, HASC>(p, e, lane, ev, so, s_stats + warp * PMRL_STATS_LEN);
+            env_step_warp<NPL, HASC, VEC>(p, e, lane, ev, so, ws);
 #pragma unroll
             for (int j = 0; j < NPL; ++j) {
-                const int a = lane + 32 * j;
+                const int a = asset_of<VEC>(lane, j);
                 if (a < A) { s_wnew[warp * A + a] = ev.a[j]; s_ea[warp * A + a] = (warp << 16) | a; }
             }
             if (lane == 0) {
@@ -189,44 +190,38 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs_fast(const
         }
     }
     if (tid == 0) bulk_wait_read<0>();
-    if (p.stats) stats_flush_block(p.stats, s_stats, kFusedWarps);
+    if (p.stats) { wstats_store(ws, s_stats + warp * PMRL_STATS_LEN, lane); stats_flush_block(p.stats, s_stats, kFusedWarps); }
 }
 
 }  // namespace pmrl
 
 using namespace pmrl;
 
-static int g_fast_variant = -1;                      // -1 = default (WT from W, RING2 off, 3 CTAs/SM)
-void pmrl_set_fast_variant(int v) { g_fast_variant = v; }
-
-template <int NPL, bool HASC, int WT, bool RING2, int MINB>
+template <int NPL, bool HASC, int VEC, int WT>
 static int launch_fast_t(StepParams& p, size_t smem, int grid, cudaStream_t s) {
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs_fast<NPL, HASC, WT, RING2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs_fast<NPL, HASC, VEC, WT, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return pmrl_fail((int)e, "cudaFuncSetAttribute(k_env_step_obs_fast) failed");
         attr_done[dev] = true;
     }
-    k_env_step_obs_fast<NPL, HASC, WT, RING2, MINB><<<grid, kFusedThreads, smem, s>>>(p);
+    k_env_step_obs_fast<NPL, HASC, VEC, WT, false, 3><<<grid, kFusedThreads, smem, s>>>(p);
     return pmrl_check_launch("k_env_step_obs_fast");
 }
 
-template <int NPL, bool HASC>
+template <int NPL, int VEC>
 static int launch_fast_w(StepParams& p, size_t smem, int grid, cudaStream_t s) {
-    if (p.W == 50) return launch_fast_t<NPL, HASC, 50, false, 3>(p, smem, grid, s);
-    if (p.W == 32) return launch_fast_t<NPL, HASC, 32, false, 3>(p, smem, grid, s);
-    return launch_fast_t<NPL, HASC, 0, false, 3>(p, smem, grid, s);
+    const bool hasc = p.commission > 0.0f;
+    if (p.W == 50) return hasc ? launch_fast_t<NPL, true, VEC, 50>(p, smem, grid, s) : launch_fast_t<NPL, false, VEC, 50>(p, smem, grid, s);
+    return hasc ? launch_fast_t<NPL, true, VEC, 0>(p, smem, grid, s) : launch_fast_t<NPL, false, VEC, 0>(p, smem, grid, s);
 }
 
-int pmrl_launch_step_obs_fast(StepParams& p, int npl, int group, int ctas_per_sm, cudaStream_t s) {
+int pmrl_launch_step_obs_fast(StepParams& p, int npl, int vec, int group, int ctas_per_sm, cudaStream_t s) {
     if (p.F != 5 || p.W > 64 || npl > 4) return -100;              // larger A: register budget of 3 CTAs/SM does not hold
     if ((size_t)p.A * p.T >= (1u << 31) || p.A >= 65536) return -100;
-    const int var = g_fast_variant;
-    const bool ab = var >= 0 && npl == 4 && p.commission <= 0.0f && p.W == 50;   // A/B variants: benchmark shape only
-    const int minb = (ab && (var & 2)) ? 2 : 3;
-    const int slots = pmrl_sm_count() * (ctas_per_sm > 0 ? ctas_per_sm : minb);
+    const int slots = pmrl_sm_count() * (ctas_per_sm > 0 ? ctas_per_sm : 3);
     int G = group > 0 ? group : kMaxGroup;
     if (G > kMaxGroup) G = kMaxGroup;
     while (G > 1 && (p.E + G - 1) / G < 2 * slots) G >>= 1;         // small batches: more, smaller groups
@@ -236,23 +231,8 @@ int pmrl_launch_step_obs_fast(StepParams& p, int npl, int group, int ctas_per_sm
     if (smem > 200 * 1024) return -100;
     const int n_groups = (p.E + G - 1) / G;
     const int grid = n_groups < slots ? n_groups : slots;
-    const bool hasc = p.commission > 0.0f;
-    if (ab) {                                        // bit0: RING2, bit1: 2 CTAs/SM (128 registers), bit2: runtime W
-        switch (var & 7) {
-            case 0: return launch_fast_t<4, false, 50, false, 3>(p, smem, grid, s);
-            case 1: return launch_fast_t<4, false, 50, true, 3>(p, smem, grid, s);
-            case 2: return launch_fast_t<4, false, 50, false, 2>(p, smem, grid, s);
-            case 3: return launch_fast_t<4, false, 50, true, 2>(p, smem, grid, s);
-            case 4: return launch_fast_t<4, false, 0, false, 3>(p, smem, grid, s);
-            case 5: return launch_fast_t<4, false, 0, true, 3>(p, smem, grid, s);
-            default: break;
-        }
-    }
-#define FAST_CASE(N) return hasc ? launch_fast_w<N, true>(p, smem, grid, s) : launch_fast_w<N, false>(p, smem, grid, s)
-    switch (npl) {
-        case 1: FAST_CASE(1);
-        case 2: FAST_CASE(2);
-        default: FAST_CASE(4);
-    }
+#define FAST_CASE(N, V) if (npl == N && vec == V) return launch_fast_w<N, V>(p, smem, grid, s)
+    FAST_CASE(1, 1); FAST_CASE(2, 1); FAST_CASE(2, 2); FAST_CASE(4, 1); FAST_CASE(4, 2); FAST_CASE(4, 4);
 #undef FAST_CASE
+    return -100;
 }

@@ -17,7 +17,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <type_traits>
-#include <atomic>
 #include "pmrl_b200.h"
 #include "pmrl_device.cuh"
 #include "env_step.cuh"
@@ -34,7 +33,7 @@ constexpr int kRtGroupNarrow = 2 * kRtWarps;       // A <= 64: two envs per warp
 struct RtEnv { int row0, shift, fresh_slot, pad; };
 struct RtFeat { float4 fv[4][2]; };
 
-template <int NPL, bool HASC, int WT>
+template <int NPL, bool HASC, int VEC, int WT>
 __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_stats[kRtWarps * PMRL_STATS_LEN];
@@ -55,7 +54,9 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
     const int n_groups = (p.E + G - 1) / G;
     const size_t row_floats = (size_t)W * 5;
     if (tid == 0) { for (int b = 0; b < 4; ++b) mbar_init(&s_rbar[b], 1); mbar_fence_init(); }
-    if (p.stats) stats_init_block(s_stats, kRtWarps); else __syncthreads();
+    WarpStats ws;
+    wstats_init(ws);
+    __syncthreads();
 
     const int fbase = (warp * W + lane) * 5, fstep = 8 * W * 5;
     const bool w0 = lane < W, w1 = lane + 32 < W;
@@ -73,12 +74,13 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
         const int e0 = grp * G;
         const int ne = min(G, p.E - e0);
         unsigned int ticket = 0;
-        if (tid == 0) ticket = atomicAdd(p.ticket, 1u);               // consumed after phase 1: its latency hides under the step
+        if (tid == 0) ticket = p.ticket ? atomicAdd(p.ticket, 1u)    // consumed after phase 1: its latency hides under the step
+                                        : (unsigned int)(grp - (int)blockIdx.x);   // no counters: static stride over the groups
         // ---------------- phase 1: one warp per env (two per warp for narrow envs: groups of up to 16) ----------------
-        auto publish = [&](int el, const EnvVectors<NPL, HASC>& ev, const StepOut& so) {
+        auto publish = [&](int el, const EnvVectors<NPL, HASC, VEC>& ev, const StepOut& so) {
 #pragma unroll
             for (int j = 0; j < NPL; ++j) {
-                const int a = lane + 32 * j;
+                const int a = asset_of<VEC>(lane, j);
                 if (a < A) { s_wnew[el * A + a] = ev.a[j]; s_ea[el * A + a] = (el << 16) | a; }
             }
             if (lane == 0) {
@@ -95,26 +97,26 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
             // A = 100.  Each warp advances two envs with their loads issued together (scalars, then vectors, then the math).
             const int el0 = warp, el1 = warp + kRtWarps;
             EnvScalars sc0, sc1;
-            EnvVectors<NPL, HASC> ev0, ev1;
+            EnvVectors<NPL, HASC, VEC> ev0, ev1;
             StepOut so;
             if (el0 < ne) env_load_scalars(p, e0 + el0, sc0);
             if (el1 < ne) env_load_scalars(p, e0 + el1, sc1);
-            if (el0 < ne) env_load_vectors<NPL, HASC>(p, e0 + el0, lane, sc0, ev0);
-            if (el1 < ne) env_load_vectors<NPL, HASC>(p, e0 + el1, lane, sc1, ev1);
-            if (el0 < ne) { env_compute_store<NPL, HASC>(p, e0 + el0, lane, sc0, ev0, so, s_stats + warp * PMRL_STATS_LEN); publish(el0, ev0, so); }
-            if (el1 < ne) { env_compute_store<NPL, HASC>(p, e0 + el1, lane, sc1, ev1, so, s_stats + warp * PMRL_STATS_LEN); publish(el1, ev1, so); }
+            if (el0 < ne) env_load_vectors<NPL, HASC, VEC>(p, e0 + el0, lane, sc0, ev0);
+            if (el1 < ne) env_load_vectors<NPL, HASC, VEC>(p, e0 + el1, lane, sc1, ev1);
+            if (el0 < ne) { env_compute_store<NPL, HASC, VEC>(p, e0 + el0, lane, sc0, ev0, so, ws); publish(el0, ev0, so); }
+            if (el1 < ne) { env_compute_store<NPL, HASC, VEC>(p, e0 + el1, lane, sc1, ev1, so, ws); publish(el1, ev1, so); }
         } else if (warp < ne) {
-            EnvVectors<NPL, HASC> ev;
+            EnvVectors<NPL, HASC, VEC> ev;
             StepOut so;
-            env_step_warp<NPL, HASC>(p, e0 + warp, lane, ev, so, s_stats + warp * PMRL_STATS_LEN);
+            env_step_warp<NPL, HASC, VEC>(p, e0 + warp, lane, ev, so, ws);
             publish(warp, ev, so);
         }
-        if (tid == 0) s_next = (int)(gridDim.x + ticket);
+        if (tid == 0) s_next = p.ticket ? (int)(gridDim.x + ticket) : grp + (int)gridDim.x;
         __syncthreads();
         const int next_grp = s_next;                                  // (rewritten only after the tile loop's barriers)
         // pull what phase 1 of the next group will read from DRAM (raw actions, scalar state) into L2 while this group
         // streams: its dependent chain scalars → addresses → vectors then runs on L2 hits
-        if (p.tma_stages && next_grp < n_groups) {
+        if (p.prefetch_next && next_grp < n_groups) {
             const int ne_next = min(G, p.E - next_grp * G);
             const size_t a_first = (size_t)next_grp * G * A;
             const int a_lines = (ne_next * A + 31) >> 5;              // 128-byte lines of the group's action rows
@@ -215,54 +217,38 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
     }
     if (tid == 0) {
         bulk_wait_read<0>();
-        // the last CTA out re-arms the counters for the next launch that uses this slot
-        __threadfence();
-        if (atomicAdd(p.ticket + 1, 1u) == gridDim.x - 1) { p.ticket[0] = 0u; p.ticket[1] = 0u; __threadfence(); }
+        // the last CTA out re-arms the batch's counters for its next launch
+        if (p.ticket) {
+            __threadfence();
+            if (atomicAdd(p.ticket + 1, 1u) == gridDim.x - 1) { p.ticket[0] = 0u; p.ticket[1] = 0u; __threadfence(); }
+        }
     }
-    if (p.stats) stats_flush_block(p.stats, s_stats, kRtWarps);
+    if (p.stats) { wstats_store(ws, s_stats + warp * PMRL_STATS_LEN, lane); stats_flush_block(p.stats, s_stats, kRtWarps); }
 }
 
 }  // namespace pmrl
 
 using namespace pmrl;
 
-// Ticket counters of the dynamic group hand-out: 64 {ticket, finished} pairs in device memory, used round-robin by
-// consecutive launches (so launches in flight on different streams do not share one) and reset by the last CTA of
-// the launch that used them.
-constexpr int kTicketSlots = 64;
-__device__ unsigned int g_rt_tickets[kTicketSlots][2];
-
-static unsigned int* next_ticket_slot() {
-    static unsigned int* base[64] = {nullptr};
-    static std::atomic<unsigned int> turn{0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!base[dev]) {
-        void* ptr = nullptr;
-        if (cudaGetSymbolAddress(&ptr, g_rt_tickets) != cudaSuccess) return nullptr;
-        base[dev] = (unsigned int*)ptr;
-    }
-    return base[dev] + 2 * (turn.fetch_add(1, std::memory_order_relaxed) % kTicketSlots);
-}
-
-template <int NPL, bool HASC, int WT>
+template <int NPL, bool HASC, int VEC, int WT>
 static int launch_rt_t(StepParams& p, size_t smem, int grid, cudaStream_t s) {
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs_rt<NPL, HASC, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs_rt<NPL, HASC, VEC, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return pmrl_fail((int)e, "cudaFuncSetAttribute(k_env_step_obs_rt) failed");
         attr_done[dev] = true;
     }
-    k_env_step_obs_rt<NPL, HASC, WT><<<grid, kRtThreads, smem, s>>>(p);
+    k_env_step_obs_rt<NPL, HASC, VEC, WT><<<grid, kRtThreads, smem, s>>>(p);
     return pmrl_check_launch("k_env_step_obs_rt");
 }
 
-template <int NPL, bool HASC>
+template <int NPL, int VEC>
 static int launch_rt_w(StepParams& p, size_t smem, int grid, cudaStream_t s) {
-    if (p.W == 50) return launch_rt_t<NPL, HASC, 50>(p, smem, grid, s);
-    return launch_rt_t<NPL, HASC, 0>(p, smem, grid, s);
+    const bool hasc = p.commission > 0.0f;
+    if (p.W == 50) return hasc ? launch_rt_t<NPL, true, VEC, 50>(p, smem, grid, s) : launch_rt_t<NPL, false, VEC, 50>(p, smem, grid, s);
+    return hasc ? launch_rt_t<NPL, true, VEC, 0>(p, smem, grid, s) : launch_rt_t<NPL, false, VEC, 0>(p, smem, grid, s);
 }
 
 // Envs per group for a batch of E envs on `slots` persistent CTAs.  A CTA's time is (rounds it runs) x (envs per group +
@@ -282,7 +268,7 @@ static int pick_group(int E, int slots, int gmax) {
     return best;
 }
 
-int pmrl_launch_step_obs_rt(StepParams& p, int npl, int group, int ctas_per_sm, cudaStream_t s) {
+int pmrl_launch_step_obs_rt(StepParams& p, int npl, int vec, int group, int ctas_per_sm, cudaStream_t s) {
     if (p.F != 5 || p.W > 64 || npl > 4 || p.A < 32) return -100;     // A >= 32: a 32-row tile spans at most two envs
     if (((size_t)p.W * p.A) % 4 != 0 || ((uintptr_t)p.hist) % 16 != 0) return -100;   // every env's ring 16-byte aligned
     if ((size_t)p.A * p.T >= (1u << 31) || p.A >= 65536) return -100;
@@ -304,14 +290,8 @@ int pmrl_launch_step_obs_rt(StepParams& p, int npl, int group, int ctas_per_sm, 
     const size_t smem = fixed + (size_t)p.ring_bufs * ring_bytes;
     const int n_groups = (p.E + G - 1) / G;
     const int grid = n_groups < slots ? n_groups : slots;
-    p.ticket = next_ticket_slot();
-    if (!p.ticket) return -100;
-    const bool hasc = p.commission > 0.0f;
-#define RT_CASE(N) return hasc ? launch_rt_w<N, true>(p, smem, grid, s) : launch_rt_w<N, false>(p, smem, grid, s)
-    switch (npl) {
-        case 1: RT_CASE(1);
-        case 2: RT_CASE(2);
-        default: RT_CASE(4);
-    }
+#define RT_CASE(N, V) if (npl == N && vec == V) return launch_rt_w<N, V>(p, smem, grid, s)
+    RT_CASE(1, 1); RT_CASE(2, 1); RT_CASE(2, 2); RT_CASE(4, 1); RT_CASE(4, 2); RT_CASE(4, 4);
 #undef RT_CASE
+    return -100;
 }

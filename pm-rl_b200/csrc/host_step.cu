@@ -15,6 +15,7 @@
 // and there are no slice boundaries at all (measured on config 4: 2.82 ms vs 2.94–3.0 ms sliced vs 3.72 serial).
 #include <cuda_runtime.h>
 #include <mutex>
+#include <string.h>
 #include "pmrl_b200.h"
 #include "host_util.h"
 
@@ -25,6 +26,7 @@ constexpr int kMaxDevices = 64;
 
 struct HostPipe {
     bool ready = false;
+    std::mutex busy;                   // held for a whole sliced call: the streams and events below are per device
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t start = nullptr, in_ev[kMaxSlices], k_ev[kMaxSlices];
 };
@@ -32,8 +34,8 @@ struct HostPipe {
 std::mutex g_mu;
 HostPipe g_pipes[kMaxDevices];
 
-// streams/events of the calling device, created on first use (the only state this library keeps besides the
-// tensor-map cache; both are per device and live for the process)
+// streams/events of the calling device, created on first use (the only state this library keeps; per device, lives
+// for the process)
 HostPipe* pipe_for_device() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
@@ -50,6 +52,16 @@ HostPipe* pipe_for_device() {
         p.ready = true;
     }
     return &p;
+}
+
+// device-visible alias of a page-locked, mapped host pointer (cudaHostAlloc / cudaHostRegister / torch pin_memory), or null
+template <typename T>
+T* mapped_alias(const T* host) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+        return (T*)at.devicePointer;
+    (void)cudaGetLastError();
+    return nullptr;
 }
 
 // slice boundaries: slices > 0 → geometric growth ×2.5 from the first; slices < 0 → |slices| equal parts.
@@ -97,35 +109,52 @@ extern "C" int pmrl_env_step_host(const PmrlEnvCfg* cfg, const PmrlTables* tbl, 
     const size_t A = (size_t)cfg->A, WA = (size_t)cfg->W * A, obs_env = WA * (size_t)cfg->F;
 
     if (slices == 0) {
-        // zero-copy path: the kernel reads the mapped host buffer itself
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, actions_host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
-            int rc = pmrl_env_step(cfg, tbl, st, (const float*)at.devicePointer, nullptr, reward, done, obs, obs_mode, stats, stream);
+        // zero-copy path: the kernel reads the mapped host actions itself and, when the result buffers are mapped too, writes
+        // reward / done straight into them (posted PCIe writes) — the call is then ONE launch and ONE synchronisation
+        if (const float* act_dev = mapped_alias(actions_host)) {
+            PmrlStepIO io;
+            memset(&io, 0, sizeof(io));
+            io.actions = act_dev; io.reward = reward; io.done = done; io.obs = obs; io.obs_mode = obs_mode; io.stats = stats;
+            float* r_dev = mapped_alias(reward_host);
+            uint8_t* d_dev = mapped_alias(done_host);
+            const bool mirrored = r_dev && d_dev;
+            if (mirrored) { io.reward_host = r_dev; io.done_host = d_dev; }
+            int rc = pmrl_env_step_io(cfg, tbl, st, &io, stream);
             if (rc != 0) return rc;
-            PMRL_CUDA(cudaMemcpyAsync(reward_host, reward, (size_t)cfg->E * sizeof(float), cudaMemcpyDeviceToHost, s), "env_step_host: D2H reward");
-            PMRL_CUDA(cudaMemcpyAsync(done_host, done, (size_t)cfg->E, cudaMemcpyDeviceToHost, s), "env_step_host: D2H done");
+            if (!mirrored) {
+                PMRL_CUDA(cudaMemcpyAsync(reward_host, reward, (size_t)cfg->E * sizeof(float), cudaMemcpyDeviceToHost, s), "env_step_host: D2H reward");
+                PMRL_CUDA(cudaMemcpyAsync(done_host, done, (size_t)cfg->E, cudaMemcpyDeviceToHost, s), "env_step_host: D2H done");
+            }
             PMRL_CUDA(cudaStreamSynchronize(s), "env_step_host: synchronize");
             return 0;
         }
-        (void)cudaGetLastError();                  // pageable memory: fall through to the copy pipeline
+        // pageable actions: fall through to the copy pipeline
     }
     HostPipe* p = pipe_for_device();
     if (!p) return pmrl_fail(PMRL_E_ARG, "env_step_host: could not create the copy streams");
+    std::lock_guard<std::mutex> busy(p->busy);        // one sliced call per device at a time (shared streams / events)
     int bounds[kMaxSlices + 2];
     const int n = slice_bounds(cfg->E, slices == 0 ? 5 : slices, bounds);
+    // on any failure: drain what is already in flight on the caller's buffers before reporting it
+    auto drain = [&](int rc) { cudaStreamSynchronize(p->copy_in); cudaStreamSynchronize(s); cudaStreamSynchronize(p->copy_out); return rc; };
+#define PMRL_CUDA_DRAIN(call, what)                                                       \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) { pmrl_fail((int)e_, what); return drain((int)e_); }       \
+    } while (0)
 
-    PMRL_CUDA(cudaEventRecord(p->start, s), "env_step_host: event record");
-    PMRL_CUDA(cudaStreamWaitEvent(p->copy_in, p->start, 0), "env_step_host: stream wait");   // earlier work on s may still read the stage
+    PMRL_CUDA_DRAIN(cudaEventRecord(p->start, s), "env_step_host: event record");
+    PMRL_CUDA_DRAIN(cudaStreamWaitEvent(p->copy_in, p->start, 0), "env_step_host: stream wait");   // earlier work on s may still read the stage
     for (int c = 0; c < n; ++c) {
         const int lo = bounds[c], cnt = bounds[c + 1] - lo;
-        PMRL_CUDA(cudaMemcpyAsync(actions_stage + lo * A, actions_host + lo * A, (size_t)cnt * A * sizeof(float),
-                                  cudaMemcpyHostToDevice, p->copy_in), "env_step_host: H2D actions");
-        PMRL_CUDA(cudaEventRecord(p->in_ev[c], p->copy_in), "env_step_host: event record");
-        PMRL_CUDA(cudaStreamWaitEvent(s, p->in_ev[c], 0), "env_step_host: stream wait");
+        PMRL_CUDA_DRAIN(cudaMemcpyAsync(actions_stage + lo * A, actions_host + lo * A, (size_t)cnt * A * sizeof(float),
+                                        cudaMemcpyHostToDevice, p->copy_in), "env_step_host: H2D actions");
+        PMRL_CUDA_DRAIN(cudaEventRecord(p->in_ev[c], p->copy_in), "env_step_host: event record");
+        PMRL_CUDA_DRAIN(cudaStreamWaitEvent(s, p->in_ev[c], 0), "env_step_host: stream wait");
 
         PmrlEnvCfg ccfg = *cfg;
         ccfg.E = cnt;
-        PmrlEnvState cst;
+        PmrlEnvState cst = *st;
         cst.value = st->value + lo;
         cst.hist = st->hist + lo * WA;
         cst.idx = st->idx + lo;
@@ -136,15 +165,16 @@ extern "C" int pmrl_env_step_host(const PmrlEnvCfg* cfg, const PmrlTables* tbl, 
         cst.ep_return = st->ep_return ? st->ep_return + lo : nullptr;
         int rc = pmrl_env_step(&ccfg, tbl, &cst, actions_stage + lo * A, nullptr, reward + lo, done + lo,
                                obs ? obs + lo * obs_env : nullptr, obs_mode, stats, stream);
-        if (rc != 0) { cudaStreamSynchronize(p->copy_in); cudaStreamSynchronize(s); return rc; }
+        if (rc != 0) return drain(rc);
 
-        PMRL_CUDA(cudaEventRecord(p->k_ev[c], s), "env_step_host: event record");
-        PMRL_CUDA(cudaStreamWaitEvent(p->copy_out, p->k_ev[c], 0), "env_step_host: stream wait");
-        PMRL_CUDA(cudaMemcpyAsync(reward_host + lo, reward + lo, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost, p->copy_out),
-                  "env_step_host: D2H reward");
-        PMRL_CUDA(cudaMemcpyAsync(done_host + lo, done + lo, (size_t)cnt, cudaMemcpyDeviceToHost, p->copy_out),
-                  "env_step_host: D2H done");
+        PMRL_CUDA_DRAIN(cudaEventRecord(p->k_ev[c], s), "env_step_host: event record");
+        PMRL_CUDA_DRAIN(cudaStreamWaitEvent(p->copy_out, p->k_ev[c], 0), "env_step_host: stream wait");
+        PMRL_CUDA_DRAIN(cudaMemcpyAsync(reward_host + lo, reward + lo, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost, p->copy_out),
+                        "env_step_host: D2H reward");
+        PMRL_CUDA_DRAIN(cudaMemcpyAsync(done_host + lo, done + lo, (size_t)cnt, cudaMemcpyDeviceToHost, p->copy_out),
+                        "env_step_host: D2H done");
     }
-    PMRL_CUDA(cudaStreamSynchronize(p->copy_out), "env_step_host: synchronize");   // last D2H is behind the last kernel
+    PMRL_CUDA_DRAIN(cudaStreamSynchronize(p->copy_out), "env_step_host: synchronize");   // last D2H is behind the last kernel
+#undef PMRL_CUDA_DRAIN
     return 0;
 }

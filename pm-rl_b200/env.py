@@ -99,6 +99,9 @@ class BatchedTradingEnv:
         if W < 2:
             raise ValueError("window_size must be >= 2 (the reference ring indexes row 1 on reset, weight_buffer.py:9-10)")
         if self.T:
+            if cfg.episode_len <= 0:
+                # rows [t0 + k, t0 + k + W) are gathered from the tables: without an episode length k would leave them
+                raise ValueError("episode_len must be > 0 when the env reads price / feature tables")
             need = int(self.t0.max().item()) + cfg.episode_len + W if E else 0
             if need > self.T:
                 raise ValueError(f"table too short: max(t0) + episode_len + W = {need} > T = {self.T}")
@@ -114,6 +117,8 @@ class BatchedTradingEnv:
         self.ep_return = torch.zeros(E, dtype=torch.float32, device=dev)
         self.reward = torch.zeros(E, dtype=torch.float32, device=dev)
         self.done = torch.zeros(E, dtype=torch.uint8, device=dev)
+        # work counters of the fused kernel's dynamic group hand-out: owned by THIS batch (two envs on two streams never share)
+        self._ticket = torch.zeros(2, dtype=torch.int32, device=dev)
         self._stats = None
         if collect_stats:
             self._stats = torch.zeros(STATS_LEN, dtype=torch.float64, device=dev)
@@ -132,7 +137,9 @@ class BatchedTradingEnv:
         self._c_tbl = _lib.PmrlTables(_lib.ptr(self.y_tm), _lib.ptr(self.feat_am))
         self._c_st = _lib.PmrlEnvState(_lib.ptr(self.value), _lib.ptr(self.hist), _lib.ptr(self.idx),
                                        _lib.ptr(self.is_full), _lib.ptr(self.t), _lib.ptr(self.t0),
-                                       _lib.ptr(self.sharpe), _lib.ptr(self.ep_return))
+                                       _lib.ptr(self.sharpe), _lib.ptr(self.ep_return), _lib.ptr(self._ticket))
+        self._io = _lib.PmrlStepIO()
+        self._p_io = C.byref(self._io)
         self._p_cfg, self._p_tbl, self._p_st = C.byref(self._c_cfg), C.byref(self._c_tbl), C.byref(self._c_st)
         self._ptr_reward, self._ptr_done, self._ptr_stats = _lib.ptr(self.reward), _lib.ptr(self.done), _lib.ptr(self._stats)
         self.reset(obs=False)
@@ -182,6 +189,58 @@ class BatchedTradingEnv:
         if rc:
             _lib.check(rc, "pmrl_env_step")
         return buf, self.reward, self.done
+
+    def step_io(self, actions, y=None, obs: bool = True, out=None, reward=None, done=None, action_sink=None,
+                value_sink=None, weight_sink=None, index_sink=None):
+        """`step` with the kernel writing straight into caller-owned rows (C-ABI pmrl_env_step_io): `reward` [E] f32 /
+        `done` [E] u8 replace the env's own buffers (e.g. the r row of a rollout slot), `action_sink` [E, A] receives the raw
+        action, `value_sink` [E] the post-step value, `weight_sink` [E, A] the post-drift weights, `index_sink` [E] i32 the
+        loader item index t0 + k — the rows RolloutBuffer.add / ReplayBuffer.add would copy (rollout_buffer.py:51-57,
+        buffer.py:31-37).  All tensors must be contiguous CUDA tensors of the exact dtype; nothing is copied or cast."""
+        a = actions
+        if not (a.is_cuda and a.dtype is torch.float32 and a.is_contiguous() and a.numel() == self.E * self.A):
+            a = a.to(device=self.device, dtype=torch.float32).reshape(self.E, self.A).contiguous()
+        if y is not None:
+            y = y.to(device=self.device, dtype=torch.float32).reshape(self.E, self.A).contiguous()
+        want_obs = obs and self.feat_am is not None
+        buf = self._obs_buffer(out) if want_obs else None
+        E, A = self.E, self.A
+        for name, t, dt, n in (("reward", reward, torch.float32, E), ("done", done, torch.uint8, E),
+                               ("action_sink", action_sink, torch.float32, E * A), ("value_sink", value_sink, torch.float32, E),
+                               ("weight_sink", weight_sink, torch.float32, E * A), ("index_sink", index_sink, torch.int32, E)):
+            if t is not None and (t.dtype is not dt or t.numel() != n or not t.is_cuda or not t.is_contiguous()):
+                raise _lib.PmrlError(f"step_io: {name} must be a contiguous CUDA {dt} tensor of {n} elements")
+        io = self._io
+        io.actions, io.y_ext = a.data_ptr(), _lib.ptr(y)
+        io.reward = reward.data_ptr() if reward is not None else self._ptr_reward
+        io.done = done.data_ptr() if done is not None else self._ptr_done
+        io.obs, io.obs_mode, io.stats = _lib.ptr(buf), (OBS_FULL if want_obs else OBS_NONE), self._ptr_stats
+        io.action_sink, io.value_sink = _lib.ptr(action_sink), _lib.ptr(value_sink)
+        io.weight_sink, io.index_sink = _lib.ptr(weight_sink), _lib.ptr(index_sink)
+        io.reward_host = io.done_host = None
+        rc = self.lib.pmrl_env_step_io(self._p_cfg, self._p_tbl, self._p_st, self._p_io, _lib.current_stream())
+        if rc:
+            _lib.check(rc, "pmrl_env_step_io")
+        return buf, (reward if reward is not None else self.reward), (done if done is not None else self.done)
+
+    def step_burst(self, actions, reward=None, done=None):
+        """K state-only steps in ONE launch on pre-supplied actions [K, E, A] (imagination bursts, HORIZON = 15 in
+        config/dreamer.py:54): returns (reward [K, E], done [K, E]); bit-identical to K calls of `step(obs=False)`."""
+        a = actions
+        if not (a.is_cuda and a.dtype is torch.float32 and a.is_contiguous() and a.dim() >= 2 and a[0].numel() == self.E * self.A):
+            a = a.to(device=self.device, dtype=torch.float32).reshape(-1, self.E, self.A).contiguous()
+        K = a.shape[0]
+        if reward is None:
+            reward = torch.empty(K, self.E, dtype=torch.float32, device=self.device)
+        if done is None:
+            done = torch.empty(K, self.E, dtype=torch.uint8, device=self.device)
+        if reward.numel() != K * self.E or done.numel() != K * self.E or reward.dtype is not torch.float32 or done.dtype is not torch.uint8:
+            raise _lib.PmrlError("step_burst: reward [K, E] float32 / done [K, E] uint8 expected")
+        rc = self.lib.pmrl_env_step_burst(self._p_cfg, self._p_tbl, self._p_st, a.data_ptr(), K, _lib.ptr(reward), _lib.ptr(done),
+                                          self._ptr_stats, _lib.current_stream())
+        if rc:
+            _lib.check(rc, "pmrl_env_step_burst")
+        return reward, done
 
     # ------------------------------------------------------------------------------------------
     def step_host(self, actions_host, reward_host=None, done_host=None, obs: bool = True, out=None, chunks: int = 0):

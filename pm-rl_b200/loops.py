@@ -15,30 +15,33 @@ import torch
 @torch.no_grad()
 def collect_on_policy(env, act_fn, buffer, num_items: int):
     """env: BatchedTradingEnv; act_fn(obs [E,A,W,F]) -> actions [E,A(,1)]; buffer: DeviceRolloutBuffer or None.
-    Runs one episode of `num_items` loader items (1 reset + num_items-1 steps).  Returns the final obs."""
+    Runs one episode of `num_items` loader items (1 reset + num_items-1 steps).  Returns the final obs.
+
+    The step kernel writes the buffer rows itself (`buffer.sinks`): reward, raw action and post-step value of item k go
+    to slot k - (W-1), and the obs the step returns — the obs stored WITH the next item (on_policy.py:65 stores the obs
+    before the step) — is materialised directly in s[slot + 1].  No copy kernel, no second obs pass, no host sync."""
     if buffer is not None:
         buffer.reset()
     s = env.reset()
     for step in range(1, num_items):
         a = act_fn(s)
-        slot = buffer.obs_slot() if buffer is not None else None
-        if slot is not None:
-            slot.copy_(s)                                   # the obs BEFORE the step is what add() stores (on_policy.py:65)
-        s_next, r, _ = env.step(a)
-        if buffer is not None:
-            buffer.add(None if slot is not None else s, a, env.value, r)
-        s = s_next
+        if buffer is None:
+            s, _, _ = env.step(a)
+        else:
+            s, _, _ = env.step_io(a, **buffer.sinks(step))
+            buffer.advance()
     return s
 
 
 @torch.no_grad()
 def collect_off_policy(env, act_fn, buffer, epoch: int, num_items: int):
-    """env: BatchedTradingEnv; buffer: DeviceReplayBuffer.  `buffer.add(epoch, step, a, r)` per item (off_policy.py:87)."""
+    """env: BatchedTradingEnv; buffer: DeviceReplayBuffer.  `buffer.add(epoch, step, a, r)` per item (off_policy.py:87),
+    with the (i, a, r) row written by the step kernel: `i` is each env's OWN loader index t0[e] + k — the row the replay
+    gather regenerates s and s' from (buffer.py:65-68) — not the lockstep counter."""
     s = env.reset()
     for step in range(1, num_items):
         a = act_fn(s)
-        s, r, _ = env.step(a)
-        buffer.add(epoch, step, a.reshape(env.E, env.A), r)
+        s, _, _ = env.step_io(a, **buffer.sinks(epoch, step))
     return s
 
 

@@ -18,7 +18,8 @@ def test_header_declares_the_documented_entry_points():
     syms = declared_symbols()
     for must in ("pmrl_env_reset", "pmrl_env_step", "pmrl_obs_build", "pmrl_ffd_weights", "pmrl_ffd_transform",
                  "pmrl_scale_series", "pmrl_pack_features", "pmrl_rollout_add", "pmrl_rollout_gather",
-                 "pmrl_replay_add", "pmrl_replay_gather", "pmrl_pg_reward_fwd_bwd", "pmrl_eval_metrics"):
+                 "pmrl_replay_add", "pmrl_replay_gather", "pmrl_pg_reward_fwd_bwd", "pmrl_eval_metrics",
+                 "pmrl_env_step_io", "pmrl_env_step_burst", "pmrl_env_step_host", "pmrl_rollout_gather_index"):
         assert must in syms
 
 
@@ -30,7 +31,19 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} is declared in include/pmrl_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared_symbols(), "ctypes signature table and header diverged"
-    assert _lib.load().pmrl_abi_version() == 2
+    assert _lib.load().pmrl_abi_version() == 3
+
+
+def test_ctypes_structs_match_the_c_layout():
+    """sizeof / field offsets of the structs that cross the boundary, as the C compiler sees them."""
+    from pmrl_b200 import _lib
+    lib = _lib.load()
+    for which, ct in ((0, _lib.PmrlEnvCfg), (1, _lib.PmrlTables), (2, _lib.PmrlEnvState), (3, _lib.PmrlStepIO)):
+        assert lib.pmrl_abi_sizeof(which) == ctypes.sizeof(ct), ct.__name__
+    assert lib.pmrl_abi_sizeof(100) == _lib.PmrlStepIO.stats.offset
+    assert lib.pmrl_abi_sizeof(101) == _lib.PmrlStepIO.done_host.offset
+    assert lib.pmrl_abi_sizeof(102) == _lib.PmrlEnvState.ticket.offset
+    assert lib.pmrl_abi_sizeof(103) == _lib.PmrlEnvCfg.initial_cash.offset
 
 
 def test_argument_validation_needs_no_gpu():
@@ -38,7 +51,7 @@ def test_argument_validation_needs_no_gpu():
     from pmrl_b200 import _lib
     lib = _lib.load()
     cfg = _lib.PmrlEnvCfg(1, 0, 8, 5, 0, 0, 0, 16, 1, 25000.0, 0.0, 1.0, 0.04)          # A = 0
-    st = _lib.PmrlEnvState(1, 1, 1, 1, 1, None, None, None)
+    st = _lib.PmrlEnvState(1, 1, 1, 1, 1, None, None, None, None)
     rc = lib.pmrl_env_step(ctypes.byref(cfg), None, ctypes.byref(st), 1, 1, 1, 1, None, 0, None, None)
     assert rc == -2 and b"A>=1" in lib.pmrl_last_error()
     assert lib.pmrl_ffd_weights(None, 1, 10, 1e-5, None, None, None) == -1

@@ -264,10 +264,85 @@ def test_collect_loops_drive_env_and_buffers():
         s = ora.obs()
     rb = DeviceReplayBuffer(env.feat_am, F, items, E, A, W, buffer_size=3 * items, batch_size=4)
     loops.collect_off_policy(env, act_fn, rb, 0, items)
-    assert int(rb.bi[0, 0, 0]) == 2 * (W - 1) and int(rb.bi[0, -1, 0]) == items - 1
+    assert int(rb.bi[0, 0, 0]) == 2 * (W - 1) and int(rb.bi[0, -1, 0]) == items - 1        # t0 = 0: loader index = lockstep counter
     total, met = loops.evaluate(env, act_fn, items)
     assert total.shape == (E,) and met.shape == (E, 4) and torch.isfinite(met).all() and torch.isfinite(total).all()
     assert np.isfinite(ora.value).all()
+
+
+def test_off_policy_collect_stores_each_envs_own_loader_index():
+    """Per-env episode offsets: the replay row index is t0[e] + k, so a sampled (s, a, r, s') regenerates exactly the
+    observations that env saw (feature channels) around the stored action — not rows of the lockstep counter."""
+    import pmrl_b200
+    from pmrl_b200 import loops, synth
+    from pmrl_b200.buffers import DeviceReplayBuffer
+    from pmrl_b200.env import BatchedTradingEnv
+    E, A, W, F, items = 7, 12, 5, 5, 40
+    tbl = synth.gbm_ohlc(256, A)
+    t0 = torch.tensor([0, 3, 17, 101, 55, 9, 200], dtype=torch.int32)
+    env = BatchedTradingEnv(pmrl_b200.EnvConfig(num_envs=E, num_assets=A, window_size=W, episode_len=items), prices=tbl, t0=t0)
+    seen, acts = [], []
+    gen = torch.Generator(device="cuda").manual_seed(3)
+
+    def act_fn(obs):
+        seen.append(obs.clone())                                  # seen[k] = obs after step k (k = 0: reset)
+        acts.append(torch.randn(E, A, generator=gen, device="cuda"))
+        return acts[-1]
+
+    rb = DeviceReplayBuffer(env.feat_am, F, items, E, A, W, buffer_size=2 * items, batch_size=4)
+    last = loops.collect_off_policy(env, act_fn, rb, 0, items)
+    seen.append(last.clone())
+    off = 2 * (W - 1)
+    steps = torch.arange(off, items, dtype=torch.int32)
+    assert torch.equal(rb.bi[0].cpu(), steps[:, None] + t0[None, :])
+    epochs = np.zeros(5, np.int64); envs = np.array([1, 3, 6, 2, 4]); starts = np.array([0, 4, 11, 20, rb.epoch_len - W - 2])
+    s, a, r, s2 = rb.gather(epochs, envs, starts)
+    for b in range(5):
+        n = int(starts[b]) + W - 1 + off                          # loader step whose row is `end - 1`
+        assert torch.equal(s[b, :, :, :F - 1], seen[n][envs[b], :, :, :F - 1]), f"s of sample {b}"
+        assert torch.equal(s2[b, :, :, :F - 1], seen[n + 1][envs[b], :, :, :F - 1]), f"s' of sample {b}"
+        assert torch.equal(a[b, :, 0], acts[n][envs[b]])         # a[:, -1] = action stored at `end` = taken at loader step n + 1
+        # channel F-1 = the action history ending at that action (buffer.py:69-70)
+        hist = torch.stack([acts[m - 1][envs[b]] for m in range(n - W + 1, n + 2)], dim=1)      # [A, W + 1]
+        assert torch.equal(s[b, :, :, F - 1], hist[:, :-1]) and torch.equal(s2[b, :, :, F - 1], hist[:, 1:])
+
+
+@pytest.mark.parametrize("A,W,E", [(12, 5, 7), (100, 50, 5), (50, 8, 9)])
+def test_index_mode_rollout_buffer_regenerates_the_stored_observations(A, W, E):
+    """mode='index' (loader index + raw action + un-wrapped weight history, 8A + 12 bytes per env-step) gathers exactly the
+    minibatch the full-storage buffer (4·A·W·F bytes per env-step, the reference layout) holds — both filled by the step
+    kernel itself through `collect_on_policy`."""
+    import pmrl_b200
+    from pmrl_b200 import loops, synth
+    from pmrl_b200.buffers import DeviceRolloutBuffer
+    from pmrl_b200.env import BatchedTradingEnv
+    F, items = 5, W + 23
+    tbl = synth.gbm_ohlc(items + W + 80, A)
+    t0 = synth.episode_offsets(E, items + W + 80, W, items)
+    cfg = pmrl_b200.EnvConfig(num_envs=E, num_assets=A, window_size=W, episode_len=items)
+    gens = [torch.Generator(device="cuda").manual_seed(8) for _ in range(2)]
+    bufs = []
+    for mode, gen in zip(("full", "index"), gens):
+        env = BatchedTradingEnv(cfg, prices=tbl, t0=t0)
+        buf = DeviceRolloutBuffer(F, items, E, A, W, batch_size=4, mode=mode, feat_am=env.feat_am, y_tm=env.y_tm)
+        c0 = env.lib.pmrl_launch_count()
+        loops.collect_on_policy(env, lambda s, gen=gen: torch.randn(E, A, generator=gen, device="cuda"), buf, items)
+        # one fused launch per item (+ the reset's two): no copy kernels in the loop
+        assert env.lib.pmrl_launch_count() - c0 == (items - 1) + 2
+        if mode == "full":
+            buf.fill_prices(env)
+        bufs.append(buf)
+    full, index = bufs
+    assert index.nbytes() * 5 < full.nbytes()
+    assert torch.equal(full.a, index.a) and torch.equal(full.v, index.v) and torch.equal(full.r, index.r)
+    rs = np.random.RandomState(0)
+    # the reference samples idx in [1, epoch_len) (rollout_buffer.py:123): the last slot of the epoch buffer is never filled
+    slots = rs.randint(1, full.S - 1, 24); envs = rs.randint(0, E, 24)
+    slots[:3] = (1, 2, full.S - 2)
+    for got, want, name in zip(index.gather(slots, envs), full.gather(slots, envs), ("s", "a", "r", "pv", "pa", "p")):
+        assert torch.equal(got, want), name
+    with pytest.raises(IndexError):
+        full.gather(np.array([0]), np.array([0]))                 # slot - 1 would be read (rollout_buffer.py:130-131)
 
 
 # ---------------------------------------------------------------- indicator windows (N3)
