@@ -27,7 +27,10 @@ def test_transform_matches_reference():
     out, widths, mw = ffd_oracle.ffd_transform(g["x"], g["d"], float(g["thres"]))
     assert mw == int(g["max_width"])
     np.testing.assert_array_equal(widths, g["widths"])
-    np.testing.assert_allclose(out, g["out"], rtol=1e-6, atol=1e-6)
+    # fp32 conv1d's summation order depends on the host's oneDNN/ISA path: the golden (one machine) and this run
+    # (another) are both within ~1 ulp of max|x| of the fp64 filter, so that is the bound between them
+    atol = 4 * np.finfo(np.float32).eps * float(np.abs(g["x"]).max())
+    np.testing.assert_allclose(out, g["out"], rtol=1e-6, atol=atol)
 
 
 def test_fp64_yardstick_close_to_fp32_reference():

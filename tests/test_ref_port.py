@@ -24,7 +24,9 @@ def run_port(d, steps=None):
 def test_port_matches_golden(name):
     d = util.load_env_fixture(name)
     env, vals, rews, obs = run_port(d)
-    util.assert_values_close(vals, d["values"], name, rtol=2e-6)
+    # the fixtures were written on another host: torch's CPU softmax/sum vector paths differ per ISA, so the
+    # cross-machine bound is the north-star 1e-5 (bit-identity is asserted against the live reference below)
+    util.assert_values_close(vals, d["values"], name)
     util.assert_rewards_close(rews, d["rewards"], name)
     assert env.ring.pos == d["idx"][-1] and env.ring.wrapped == bool(d["is_full"][-1])
     np.testing.assert_allclose(obs[:, :, -1].numpy(), d["obs_w"][-1], rtol=1e-5, atol=1e-7)
