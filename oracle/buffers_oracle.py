@@ -3,8 +3,11 @@
   RolloutOracle  restates replay/rollout_buffer.py:7-142 for ONE env (exactly the reference's shapes);
                  PINNED by tests/golden/rollout_buffer.npz (live reference RolloutBuffer, importable here).
   replay_gather  restates the per-sample body of ReplayBuffer.sample, replay/buffer.py:58-77 (identical in
-                 replay/traj_buffer.py:68-87).  The reference module itself is not importable (it imports the
-                 non-existent `loader.data_loader`, buffer.py:4) → parity UNPINNED beyond this restatement.
+                 replay/traj_buffer.py:68-87);  ReplayOracle restates `add` (buffer.py:23-38 / traj_buffer.py:26-43) and the
+                 two samplers' draw sequences (buffer.py:45-49, traj_buffer.py:52-60).
+                 PINNED by tests/golden/replay_buffer.npz: both reference classes executed UNMODIFIED by
+                 tests/golden/make_golden_replay.py behind a stub for their one missing import (`loader.data_loader`,
+                 buffer.py:4) and the constants no config defines (PERCENT_LATEST).
 """
 from __future__ import annotations
 
@@ -61,3 +64,49 @@ def replay_gather(feat, bi, ba, br, epoch, env, start, W):
     s[..., -1] = a_hist[:, :-1]                                                   # :69
     s2[..., -1] = a_hist[:, 1:]                                                   # :70
     return s, a_hist[:, -1:].astype(np.float32), r.astype(np.float32), s2         # :72
+
+
+class ReplayOracle:
+    """replay/buffer.py:6-38 and replay/traj_buffer.py:6-43 for ONE env: the (i, a, r) index-replay rows."""
+
+    def __init__(self, train_len, A, W, buffer_size, batch_size, percent_latest=0.5):
+        self.A, self.W, self.bs = A, W, batch_size
+        self.step_offset = 2 * (W - 1)                                            # :11
+        self.epoch_len = train_len - self.step_offset                             # :12
+        self.max_epoch = buffer_size // self.epoch_len                            # :13
+        self.n_last = int(percent_latest * batch_size)                            # buffer.py:14
+        self.i = np.zeros((self.max_epoch, self.epoch_len, 1), np.float32)        # the reference stores i as f32 (Q14)
+        self.a = np.zeros((self.max_epoch, self.epoch_len, A), np.float32)
+        self.r = np.zeros((self.max_epoch, self.epoch_len, 1, 1), np.float32)
+        self.curr_epoch, self.newest_epoch, self.full = 0, 0, False
+
+    def add(self, e, i, a, r):
+        if i < self.W - 1:                                                        # :31
+            return
+        ep = int(e % self.max_epoch)
+        self.curr_epoch = ep                                                      # traj_buffer.py:35
+        self.newest_epoch = max(self.newest_epoch, ep)                            # buffer.py:38
+        step = i - self.step_offset                                               # may be negative: wraps like torch indexing
+        self.i[ep, step] = i; self.a[ep, step] = np.asarray(a).reshape(self.A); self.r[ep, step] = np.asarray(r).reshape(1)
+        if not self.full and ep == self.max_epoch - 1:                            # traj_buffer.py:42
+            self.full = True
+
+    def draws(self, sampler):
+        """The (epochs, starts) a `sample()` call draws from torch's global RNG, in the reference's call order."""
+        import torch
+        L, W, B = self.epoch_len, self.W, self.bs
+        if sampler == "traj":                                                     # traj_buffer.py:52-60
+            n = self.max_epoch if self.full else self.curr_epoch
+            ep = torch.cat([torch.tensor([self.curr_epoch]), torch.randperm(n)[:B - 1]])
+            st = torch.randint(0, L - W - 1, (1,)).repeat(B)
+        else:                                                                     # buffer.py:45-49
+            ep = torch.cat((torch.tensor([self.newest_epoch] * self.n_last, dtype=torch.long),
+                            torch.randint(0, self.newest_epoch + 1, (B - self.n_last,))))
+            st = torch.randint(0, L - W - 1, (B,))
+        return ep.numpy(), st.numpy()
+
+    def sample(self, table, sampler):
+        ep, st = self.draws(sampler)
+        bi = self.i[..., 0].astype(np.int64)[..., None]; br = self.r[..., 0, 0][..., None]
+        out = [replay_gather(table, bi, self.a[:, :, None, :], br, int(e), 0, int(s0), self.W) for e, s0 in zip(ep, st)]
+        return tuple(np.stack([o[j] for o in out]) for j in range(4)), ep, st

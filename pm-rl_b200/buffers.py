@@ -229,6 +229,7 @@ class DeviceReplayBuffer:
         self.ba = torch.zeros(P, L, E, A, device=dev)
         self.br = torch.zeros(P, L, E, device=dev)
         self.curr_epoch = 0
+        self.newest_epoch = 0                                    # buffer.py:38 `self.epoch = max(self.epoch, epoch)`
         self.full = False
 
     def __len__(self):
@@ -242,6 +243,7 @@ class DeviceReplayBuffer:
         if lockstep < self.W - 1:
             return
         self.curr_epoch = int(e % self.max_epoch)
+        self.newest_epoch = max(self.newest_epoch, self.curr_epoch)
         step = lockstep - self.step_offset
         if step < 0 or step >= self.epoch_len:
             # the reference would wrap a negative index into the tail of the epoch row (torch indexing); rows
@@ -265,6 +267,7 @@ class DeviceReplayBuffer:
         if step < self.W - 1:
             return {}
         self.curr_epoch = int(e % self.max_epoch)
+        self.newest_epoch = max(self.newest_epoch, self.curr_epoch)
         slot = step - self.step_offset
         if slot < 0 or slot >= self.epoch_len:
             return {}
@@ -290,14 +293,34 @@ class DeviceReplayBuffer:
         _lib.check(rc, "pmrl_replay_gather")
         return s, a, r, s2
 
-    def sample(self, generator=None):
-        """traj_buffer.py:45-89: epochs = [current] + random others, one random start shared by the batch; envs uniform."""
-        n_avail = self.max_epoch if self.full else self.curr_epoch + 1
-        B = self.batch_size
-        g = generator
-        epochs = torch.randint(0, n_avail, (B,), generator=g)
-        if self.include_last:
-            epochs[0] = self.curr_epoch
-        start = int(torch.randint(0, self.epoch_len - self.W - 1, (1,), generator=g))
-        envs = torch.randint(0, self.E, (B,), generator=g)
-        return self.gather(epochs, envs, torch.full((B,), start))
+    def sample(self, generator=None, sampler: str = "traj", percent_latest: float = 0.5):
+        """`ReplayBuffer.sample` with the reference's own draw sequence, so that with E == 1 and the same torch RNG state
+        it returns exactly the reference's batch:
+
+        sampler="traj"    replay/traj_buffer.py:52-60 (the class train/off_policy.py:10 imports): epochs = [current] +
+                          randperm(stored epochs)[:B-1], ONE random start shared by the batch;
+        sampler="buffer"  replay/buffer.py:45-49: int(percent_latest·B) copies of the newest epoch + randint epochs, one
+                          random start per sample.
+        Envs (the batch axis the reference does not have) are drawn last, uniformly, and only when E > 1."""
+        B, L, W, g = self.batch_size, self.epoch_len, self.W, generator
+        if sampler == "traj":
+            n = self.max_epoch if self.full else self.curr_epoch                                  # traj_buffer.py:52
+            if not self.include_last:
+                raise _lib.PmrlError("INCLUDE_LAST = False removes curr_epoch from the choices (traj_buffer.py:53-54) "
+                                     "and then indexes it anyway; only include_last=True is supported")
+            rand = torch.randperm(n, generator=g)[:B - 1]                                          # :56
+            epochs = torch.cat([torch.tensor([self.curr_epoch]), rand])                            # :57
+            if epochs.numel() < B:
+                raise IndexError(f"traj sampler: {n} stored epochs cannot fill a batch of {B} (traj_buffer.py:67 would index "
+                                 "past `epochs`)")
+            starts = torch.randint(0, L - W - 1, (1,), generator=g).repeat(B)                      # :59
+        elif sampler == "buffer":
+            n_last = int(percent_latest * B)                                                       # buffer.py:14
+            last = torch.tensor([self.newest_epoch] * n_last, dtype=torch.long)                    # :45
+            rand = torch.randint(0, self.newest_epoch + 1, (B - n_last,), generator=g)             # :46
+            epochs = torch.cat((last, rand))
+            starts = torch.randint(0, L - W - 1, (B,), generator=g)                                # :48
+        else:
+            raise ValueError("sampler must be 'traj' or 'buffer'")
+        envs = torch.randint(0, self.E, (B,), generator=g) if self.E > 1 else torch.zeros(B, dtype=torch.long)
+        return self.gather(epochs, envs, starts)

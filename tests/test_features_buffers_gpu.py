@@ -183,8 +183,33 @@ def test_replay_add_and_gather_vs_oracle():
         ws, wa, wr, ws2 = replay_gather(tbl.numpy(), bi, ba, br, epochs[b], envs[b], starts[b], W)
         np.testing.assert_array_equal(s[b].cpu().numpy(), ws); np.testing.assert_array_equal(s2[b].cpu().numpy(), ws2)
         np.testing.assert_array_equal(a[b].cpu().numpy(), wa); np.testing.assert_array_equal(r[b].cpu().numpy(), wr)
-    s, a, r, s2 = buf.sample(torch.Generator().manual_seed(0))
+    with pytest.raises(IndexError):                      # 3 stored epochs cannot fill 8 rows (traj_buffer.py:56-57,67)
+        buf.sample(torch.Generator().manual_seed(0))
+    s, a, r, s2 = buf.sample(torch.Generator().manual_seed(0), sampler="buffer")
     assert s.shape == (8, A, W, F) and a.shape == (8, A, 1) and r.shape == (8, 1, 1) and s2.shape == (8, A, W, F)
+
+
+@pytest.mark.parametrize("tag,sampler", [("buf", "buffer"), ("traj", "traj")])
+def test_replay_buffer_matches_reference_golden(tag, sampler):
+    """pmrl_replay_add / pmrl_replay_gather and the two samplers against replay/buffer.py and replay/traj_buffer.py run
+    unmodified (tests/golden/make_golden_replay.py): stored rows and sampled (s, a, r, s') bit-exact at E = 1."""
+    from pmrl_b200.buffers import DeviceReplayBuffer
+    g = golden("replay_buffer.npz")
+    A, W, F, TL, B = (int(g[k]) for k in ("A", "W", "F", "train_len", "batch"))
+    L = TL - 2 * (W - 1)
+    feat_am = torch.from_numpy(g["table"]).permute(1, 0, 2).contiguous().cuda()
+    buf = DeviceReplayBuffer(feat_am, F, TL, 1, A, W, buffer_size=int(g["epochs_kept"]) * L, batch_size=B)
+    for e in range(int(g["n_epochs"])):
+        for step in range(1, TL):
+            buf.add(e, step, torch.from_numpy(g["acts"][e, step]).cuda(), torch.from_numpy(g["rews"][e, step:step + 1]).cuda())
+    np.testing.assert_array_equal(buf.bi.cpu().numpy()[..., 0], g[f"{tag}_i"][..., 0].astype(np.int32))
+    np.testing.assert_array_equal(buf.ba.cpu().numpy()[:, :, 0], g[f"{tag}_a"])
+    np.testing.assert_array_equal(buf.br.cpu().numpy()[..., 0], g[f"{tag}_r"][..., 0, 0])
+    for k in range(3):
+        torch.manual_seed(100 + k)
+        s, a, r, s2 = buf.sample(sampler=sampler, percent_latest=float(g["percent_latest"]))
+        np.testing.assert_array_equal(s.cpu().numpy(), g[f"{tag}{k}_s"]); np.testing.assert_array_equal(s2.cpu().numpy(), g[f"{tag}{k}_s2"])
+        np.testing.assert_array_equal(a.cpu().numpy(), g[f"{tag}{k}_a"]); np.testing.assert_array_equal(r.cpu().numpy(), g[f"{tag}{k}_r"])
 
 
 # ---------------------------------------------------------------- PG reward (fwd + grad) and eval metrics

@@ -70,7 +70,7 @@ def main():
     print(json.dumps({"bench": "config3 collect: fused step(obs) + replay add", "envs": E, "assets": A, "ms_per_step": ms_c,
                       "asset_steps_per_s": E * A / ms_c * 1e3}))
     g = torch.Generator().manual_seed(0)
-    ms_g = timeit(lambda: rb.sample(g), n=20)
+    ms_g = timeit(lambda: rb.sample(g, sampler="buffer"), n=20)
     print(json.dumps({"bench": "replay sample (B = 64: s, a, r, s')", "ms": ms_g,
                       "GBps": 2 * 64 * A * W * 5 * 4 / ms_g / 1e6}))
 
