@@ -14,7 +14,20 @@ import importlib
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("PMRL_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def locate() -> str | None:
+    """the reference tree is looked for at $PMRL_REFERENCE_ROOT, `/root/reference` (the build
+    container) and `baseline/_ref/` (it is not pip-installable — no setup.py / pyproject.toml — so that directory only
+    exists if an operator puts a checkout there).  None when no candidate holds env/sim/trading_env.py."""
+    for cand in (os.environ.get("PMRL_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "env", "sim", "trading_env.py")):
+            return cand
+    return None
+
+
+REFERENCE_ROOT = locate() or "/root/reference"
 
 
 def available() -> bool:
@@ -64,3 +77,19 @@ def load_rollout_buffer_module(num_assets: int, window: int, batch_size: int):
     import replay.rollout_buffer as rb
     importlib.reload(rb)
     return rb
+
+
+def load_pg_agent(num_assets: int, window: int, features: int, seed: int = 0):
+    """The reference's on-policy agent, `agent.pg.pg.PG(F)` with its LSRE-CANN policy (net/lsre_cann.py), seeded, eval mode."""
+    _ensure_path()
+    import torch
+    import config.base as cb
+    cb.NUM_ASSETS, cb.WINDOW_SIZE = int(num_assets), int(window)
+    import net.lsre_cann as net
+    import agent.pg.pg as pg
+    importlib.reload(net)
+    importlib.reload(pg)
+    torch.manual_seed(seed)
+    agent = pg.PG(features)
+    agent.training_mode(False)
+    return agent

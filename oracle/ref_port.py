@@ -95,36 +95,67 @@ class RefPortEnv:
         return r, features
 
 
-def time_port(assets: int, window: int, steps: int, warmup: int = 50, features: int = 5, seed: int = 0):
-    """Steps/s of one RefPortEnv on one thread (pre-materialised features / price relatives, like BASELINE.md §3)."""
+def time_env(kind: str, assets: int, window: int, steps: int, warmup: int = 50, features: int = 5, seed: int = 0,
+             commission: float = 0.0, policy: bool = False):
+    """Steps/s of ONE reference env on one thread: pre-materialised features / price relatives, raw
+    N(0,1) scores as actions (the softmax branch, like the GPU arm's "random actions").
+
+    kind="live": the reference's own `env.sim.trading_env.TradingEnv` (tree found by oracle/live_reference.locate();
+                 for commission > 0 the one broken call at trading_env.py:72 is patched to relu, see live_reference).
+    kind="port": RefPortEnv above (the same torch ops in the same order) — what runs where the tree is absent.
+    policy=True: BASELINE config 1 — the reference's PG agent (LSRE-CANN policy) produces every action from the
+                 observation, as in train/on_policy.py:59-67 (live only)."""
     import time
     torch.set_num_threads(1)
     g = torch.Generator().manual_seed(seed)
-    env = RefPortEnv(assets, window)
+    agent = None
+    if kind == "live":
+        from oracle import live_reference as live
+        te = live.load_env_module(assets, window, commission, patch_maximum=commission > 0)
+        env = te.TradingEnv()
+        if policy:
+            agent = live.load_pg_agent(assets, window, features, seed)
+    else:
+        if policy:
+            raise RuntimeError("the PG policy is reference code (agent/pg, net/lsre_cann) and needs the live tree")
+        env = RefPortEnv(assets, window, commission=commission)
     feat = torch.rand(assets, window, features, generator=g)
     n = 64
-    acts = torch.softmax(torch.randn(n, 1, assets, 1, generator=g), dim=2)
+    acts = torch.randn(n, 1, assets, 1, generator=g)
     ys = 1.0 + 0.01 * torch.randn(n, assets, generator=g)
-    env.reset(feat)
+    s_obs = env.reset(feat)
+
+    def one(s, s_obs):
+        a = agent.act(s_obs) if agent is not None else acts[s % n]
+        return env.step(a, feat, ys[s % n])[1]
+
     for s in range(warmup):
-        env.step(acts[s % n], feat, ys[s % n])
+        s_obs = one(s, s_obs)
     t0 = time.perf_counter()
     for s in range(steps):
         if s % 1000 == 999:
-            env.reset(feat)                      # keeps the info lists bounded like an episode boundary
-        env.step(acts[s % n], feat, ys[s % n])
+            s_obs = env.reset(feat)              # keeps the info lists bounded like an episode boundary
+        s_obs = one(s, s_obs)
     dt = time.perf_counter() - t0
     return steps / dt
 
 
+def time_port(assets: int, window: int, steps: int, warmup: int = 50, features: int = 5, seed: int = 0):
+    return time_env("port", assets, window, steps, warmup, features, seed)
+
+
 def _worker(args):
-    return time_port(*args)
+    return time_env(*args)
 
 
-def time_port_all_cores(assets: int, window: int, steps: int, procs: int):
+def time_all_cores(kind: str, assets: int, window: int, steps: int, procs: int, commission: float = 0.0, policy: bool = False):
     """Sum of steps/s over `procs` independent single-thread processes."""
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     with ctx.Pool(procs) as pool:
-        rates = pool.map(_worker, [(assets, window, steps, 50, 5, i) for i in range(procs)])
+        rates = pool.map(_worker, [(kind, assets, window, steps, 50, 5, i, commission, policy) for i in range(procs)])
     return sum(rates), rates
+
+
+def time_port_all_cores(assets: int, window: int, steps: int, procs: int):
+    return time_all_cores("port", assets, window, steps, procs)

@@ -182,7 +182,11 @@ class TradingEnv:
 
     @property
     def value(self):
-        return self._env.value[0]
+        """`self.value` of the reference: INITIAL_CASH (a float) after reset (:27), then the 0-dim value tensor of the last
+        step ON THE CALLER'S DEVICE (:89) — a CPU caller gets a host tensor, so `RolloutBuffer.add(..., env.value, r)` →
+        `np.array(v)` (rollout_buffer.py:55) works as it does on the reference."""
+        t = self._trace["values"]
+        return t[-1] if t else float(self.cfg.initial_cash)
 
     def _write_weights(self, features):
         A, W, F = self._env.A, self._env.W, self._env.F

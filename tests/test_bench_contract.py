@@ -37,8 +37,20 @@ def test_reference_arm_prints_the_contract_line():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in line, k
     assert line["impl"] == "reference" and line["value"] > 0 and line["config"]["workload"] == "c2"
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import live_reference as live
+    want_kind = "reference" if live.locate() else "port"                # the live tree first, else the port
+    assert line["cpu_baseline"]["kind"] == want_kind and line["cpu_baseline"]["cores"] >= 1
+    cfg = bench.shared_config(type("A", (), dict(workload="c2", envs=0, tune=[], graph=0, burst=0))(), 1)
+    assert line["config"] == cfg                                        # both arms print the same config object
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_falls_back_to_the_port_without_the_tree():
+    env = dict(os.environ, PMRL_BENCH_REF_SECONDS="0.2", PMRL_REFERENCE_ROOT="/nonexistent")
+    code = ("import sys; sys.path.insert(0, %r); from oracle import live_reference as live; live.locate = lambda: None; import bench; "
+            "print(bench.cpu_baseline(11, 8, 0.0, seconds=0.2, context=False)['kind'])" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().splitlines()[-1] == "port", out.stderr[-2000:]
 
 
 def test_reference_arm_other_ranks_exit_without_work():
