@@ -573,7 +573,7 @@ def main():
     ap.add_argument("--burst", type=int, default=0, metavar="K",
                     help="state-only workloads: advance K steps per launch through pmrl_env_step_burst (imagination bursts)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VAL",
-                    help="kernel launch-shape override: group|ctas|fast|rt = int (pmrl_set_tuning)")
+                    help="kernel launch-shape override: group|ctas|fast|rt|staged = int (pmrl_set_tuning)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -598,7 +598,7 @@ def main():
             os.sched_setaffinity(0, cores[ctx.local_rank * per:(ctx.local_rank + 1) * per])
     except Exception:
         pass
-    tune_keys = {"group": _lib.TUNE_GROUP_ENVS, "ctas": _lib.TUNE_CTAS_PER_SM, "fast": _lib.TUNE_FAST_FILL, "rt": _lib.TUNE_RING_TMA}
+    tune_keys = {"group": _lib.TUNE_GROUP_ENVS, "ctas": _lib.TUNE_CTAS_PER_SM, "fast": _lib.TUNE_FAST_FILL, "rt": _lib.TUNE_RING_TMA, "staged": _lib.TUNE_STAGED}
     for kv in args.tune:
         k, v = kv.split("=")
         _lib.set_tuning(tune_keys[k], int(v))

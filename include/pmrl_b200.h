@@ -162,6 +162,10 @@ const char* pmrl_last_error(void);
 #define PMRL_TUNE_RING_TMA    11  /* 1 (default): fused kernel that loads each env's weight ring with one TMA bulk copy
                                      (env_step_rt.cu); 2: the same without the next-group L2 prefetch; 0: register ring loads
                                      (env_step_fast.cu) */
+#define PMRL_TUNE_STAGED      12  /* 1 (default): state-only step of wide envs (A > 128, A % 4 == 0) with the action / previous-weight /
+                                     price-relative rows staged one env ahead through shared memory by TMA bulk copies
+                                     (env_step_staged.cu) when a warp has more than one env; 2: also for small batches; 0: register loads +
+                                     L2 prefetch (k_env_step) */
 int pmrl_set_tuning(int32_t key, int32_t value);
 
 /* Kernels this library has launched in this process so far (every entry point counts its own launches; bench.py reports

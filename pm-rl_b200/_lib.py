@@ -137,7 +137,7 @@ def current_stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-TUNE_GROUP_ENVS, TUNE_CTAS_PER_SM, TUNE_FUSED, TUNE_FAST_FILL, TUNE_RING_TMA = 2, 3, 4, 5, 11
+TUNE_GROUP_ENVS, TUNE_CTAS_PER_SM, TUNE_FUSED, TUNE_FAST_FILL, TUNE_RING_TMA, TUNE_STAGED = 2, 3, 4, 5, 11, 12
 
 
 def set_tuning(key: int, value: int) -> None:

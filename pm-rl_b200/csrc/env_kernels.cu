@@ -360,7 +360,14 @@ static int dispatch_npl_vec(int npl, int vec, Fn&& f) {
     return pmrl_fail(PMRL_E_SHAPE, "unsupported (slots per lane, vector width)");
 }
 
+static int g_tune_staged = 1;
+
 static int launch_step_s(const StepParams& p, int npl, int vec, cudaStream_t s) {
+    if (g_tune_staged && npl >= 8 && (g_tune_staged == 2 || (p.E + kStepWarps - 1) / kStepWarps > pmrl_sm_count() * 2)) {
+        // wide envs, more than one env per warp: rows staged one env ahead through shared memory (env_step_staged.cu)
+        const int rc = pmrl_launch_step_staged(p, npl, vec, g_tune_ctas_per_sm, s);
+        if (rc != -100) return rc;
+    }
     const int want = (p.E + kStepWarps - 1) / kStepWarps;
     const int cap = pmrl_sm_count() * 8;
     const int grid = want < cap ? want : cap;
@@ -408,6 +415,7 @@ extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
         case PMRL_TUNE_FUSED: g_tune_fused = value; return 0;
         case PMRL_TUNE_FAST_FILL: g_tune_fast = value; return 0;
         case PMRL_TUNE_RING_TMA: g_tune_rt = value; return 0;
+        case PMRL_TUNE_STAGED: g_tune_staged = value; return 0;
         default: return pmrl_fail(PMRL_E_ARG, "unknown tuning key");
     }
 }

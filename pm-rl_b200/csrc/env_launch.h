@@ -9,3 +9,7 @@ int pmrl_launch_step_obs_rt(pmrl::StepParams& p, int npl, int vec, int group, in
 
 // Register-staged fused step+obs kernel (env_step_fast.cu).  Returns -100 if the shape is not covered.
 int pmrl_launch_step_obs_fast(pmrl::StepParams& p, int npl, int vec, int group, int ctas_per_sm, cudaStream_t s);
+
+// State-only step for wide envs with the rows staged through shared memory by TMA bulk copies (env_step_staged.cu).
+// Returns -100 if the shape is not covered.
+int pmrl_launch_step_staged(const pmrl::StepParams& p, int npl, int vec, int shape, cudaStream_t s);

@@ -135,6 +135,12 @@ __device__ __forceinline__ void ld_plain_v(const float* p, float* d) {       // 
     else d[0] = *p;
 }
 template <int VEC>
+__device__ __forceinline__ void lds_v(uint32_t saddr, float* d) {            // staged rows (env_step_staged.cu): ld.shared
+    if constexpr (VEC == 4) asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "r"(saddr));
+    else if constexpr (VEC == 2) asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(d[0]), "=f"(d[1]) : "r"(saddr));
+    else asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d[0]) : "r"(saddr));
+}
+template <int VEC>
 __device__ __forceinline__ void st_v(float* p, const float* s) {
     if constexpr (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(s[0], s[1], s[2], s[3]);
     else if constexpr (VEC == 2) *reinterpret_cast<float2*>(p) = make_float2(s[0], s[1]);
@@ -279,10 +285,20 @@ __device__ __forceinline__ void env_prefetch_vectors(const StepParams& p, int e,
 // One transition of env e on the rows in va / vy / vwl.  On return va[] holds w' (the post-drift weights, in the asset
 // map above).  STORE_STATE = false leaves the scalar state (V, ring pointer, local step, episode return) in `out` only —
 // the burst kernel writes it back once per burst; reward / done / the ring row / the sinks are always written.
-template <int NPL, bool HASC, int VEC, bool TAIL = false, bool LOADY = true, bool STORE_STATE = true>
+struct NoHook { __device__ __forceinline__ void before_y() const {} __device__ __forceinline__ void after_y() const {} };
+
+// WLS: the previous weights are not held in registers through the mu iteration but re-read from their staged shared-memory
+// row (`wl_stage`) in every iteration (env_step_staged.cu, single-stage shape: 16 fewer live registers → more resident warps).
+// `hook.before_y()` / `hook.after_y()` bracket the late read of the price relatives (LOADY = false) so the staging kernel
+// can wait for / refill that row.
+// YSTAGE: the late price-relative read always comes from `y_stage` (no runtime source test per group).  NOSINKS: the launcher
+// has checked that no PmrlStepIO sink / host mirror is set, so their per-env null tests are compiled out.
+template <int NPL, bool HASC, int VEC, bool TAIL = false, bool LOADY = true, bool STORE_STATE = true, bool WLS = false, typename Hook = NoHook,
+          bool YSTAGE = false, bool NOSINKS = false>
 __device__ __forceinline__ void env_compute_rows(const StepParams& p, int e, int lane, const EnvScalars& sc,
-                                                 float (&va)[NPL], float (&vy)[NPL], float (&vwl)[HASC ? NPL : 1],
-                                                 StepOut& out, WarpStats& ws) {
+                                                 float (&va)[NPL], float (&vy)[NPL], float (&vwl)[(HASC && !WLS) ? NPL : 1],
+                                                 StepOut& out, WarpStats& ws, uint32_t y_stage = 0u, uint32_t wl_stage = 0u,
+                                                 const Hook& hook = Hook()) {
     const int A = p.A, W = p.W;
     float* __restrict__ hist_e = p.hist + (size_t)e * W * A;
 
@@ -321,7 +337,7 @@ __device__ __forceinline__ void env_compute_rows(const StepParams& p, int e, int
 
     // the raw action row of a rollout / replay slot (replay/rollout_buffer.py:53, replay/buffer.py:35), written by the
     // kernel that read it instead of a separate copy
-    if (p.action_sink) {
+    if (!NOSINKS && p.action_sink) {
 #pragma unroll
         for (int g = 0; g < NPL / VEC; ++g)
             if (slot_ok<NPL, VEC, TAIL>(g * VEC, lane, A)) st_v<VEC>(p.action_sink + (size_t)e * A + (g * 32 + lane) * VEC, &va[g * VEC]);
@@ -373,7 +389,9 @@ __device__ __forceinline__ void env_compute_rows(const StepParams& p, int e, int
     if (HASC) {
         const float c = p.commission;
         const float w0 = __shfl_sync(PMRL_FULL_MASK, va[0], 0);
-        const float wl0 = __shfl_sync(PMRL_FULL_MASK, vwl[0], 0);
+        float wl0;
+        if constexpr (WLS) { float t0[1]; lds_v<1>(wl_stage, t0); wl0 = t0[0]; }
+        else wl0 = __shfl_sync(PMRL_FULL_MASK, vwl[0], 0);
         const float denom = __fsub_rn(1.0f, __fmul_rn(c, w0));
         const float cw = __fmul_rn(c, wl0);
         float mu_last = 1.0f, mu = p.mu0;
@@ -383,11 +401,30 @@ __device__ __forceinline__ void env_compute_rows(const StepParams& p, int e, int
         // inside the iteration.  relu is evaluated as (d + |d|) / 2: d + |d| is 2d or 0 exactly and a sum of doubled
         // terms is the doubled sum bit for bit, so halving the total restores Σ relu(d) in the same rounding sequence
         // with two packed instructions per pair instead of two FMNMX and one packed add.
-        if (lane == 0) vwl[0] = -1e30f;
+        if (!WLS && lane == 0) vwl[0] = -1e30f;
         while (fabsf(__fsub_rn(mu, mu_last)) > 1e-10f && it < p.mu_max_iter) {
             mu_last = mu;
             float part;
-            if constexpr (NPL == 1) {
+            if constexpr (WLS) {
+                static_assert(!WLS || VEC == 4, "staged previous weights need the 16-byte asset map");
+                const float2 mu2 = make_float2(mu, mu), neg1 = make_float2(-1.0f, -1.0f);
+                float t[NPL];
+#pragma unroll
+                for (int g = 0; g < NPL / VEC; ++g) {
+                    float w4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    if (slot_ok<NPL, VEC, TAIL>(g * VEC, lane, A)) lds_v<4>(wl_stage + 16u * (uint32_t)(g * 32 + lane), w4);
+                    if (g == 0 && lane == 0) w4[0] = -1e30f;
+#pragma unroll
+                    for (int h = 0; h < 4; h += 2) {
+                        const int j = g * 4 + h;
+                        const float2 m = __fmul2_rn(mu2, make_float2(va[j], va[j + 1]));
+                        const float2 d = __ffma2_rn(m, neg1, make_float2(w4[h], w4[h + 1]));
+                        const float2 r2 = __fadd2_rn(d, make_float2(fabsf(d.x), fabsf(d.y)));
+                        t[j] = r2.x; t[j + 1] = r2.y;
+                    }
+                }
+                part = __fmul_rn(lane_sum(t), 0.5f);
+            } else if constexpr (NPL == 1) {
                 part = fmaxf(__fsub_rn(vwl[0], __fmul_rn(mu, va[0])), 0.0f);
             } else {
                 const float2 mu2 = make_float2(mu, mu), neg1 = make_float2(-1.0f, -1.0f);
@@ -410,18 +447,21 @@ __device__ __forceinline__ void env_compute_rows(const StepParams& p, int e, int
     }
 
     if constexpr (!LOADY) {                                      // price relatives fetched late (see env_load_rows)
-        const bool ext = p.y_ext != nullptr;
-        const float* __restrict__ yrow = env_y_row(p, e, sc);
+        hook.before_y();
+        const bool ext = !YSTAGE && p.y_ext != nullptr;
+        const float* __restrict__ yrow = YSTAGE ? nullptr : env_y_row(p, e, sc);
 #pragma unroll
         for (int g = 0; g < NPL / VEC; ++g) {
             const int a = (g * 32 + lane) * VEC;
             if (slot_ok<NPL, VEC, TAIL>(g * VEC, lane, A)) {
-                if (ext) ld_once_v<VEC>(yrow + a, &vy[g * VEC]); else ld_keep_v<VEC>(yrow + a, &vy[g * VEC]);
+                if (YSTAGE) lds_v<VEC>(y_stage + 4u * (uint32_t)a, &vy[g * VEC]);         // row staged in shared memory by a bulk copy
+                else if (ext) ld_once_v<VEC>(yrow + a, &vy[g * VEC]); else ld_keep_v<VEC>(yrow + a, &vy[g * VEC]);
             } else {
 #pragma unroll
                 for (int c = 0; c < VEC; ++c) vy[g * VEC + c] = 0.0f;
             }
         }
+        hook.after_y();
     }
 
     // ---- value, drift, return (trading_env.py:78-90) ----
@@ -459,7 +499,7 @@ __device__ __forceinline__ void env_compute_rows(const StepParams& p, int e, int
     for (int g = 0; g < NPL / VEC; ++g)
         if (slot_ok<NPL, VEC, TAIL>(g * VEC, lane, A)) {
             st_v<VEC>(hist_e + (size_t)i * A + (g * 32 + lane) * VEC, &va[g * VEC]);
-            if (p.weight_sink) st_v<VEC>(p.weight_sink + (size_t)e * A + (g * 32 + lane) * VEC, &va[g * VEC]);   // un-wrapped history row
+            if (!NOSINKS && p.weight_sink) st_v<VEC>(p.weight_sink + (size_t)e * A + (g * 32 + lane) * VEC, &va[g * VEC]);   // un-wrapped history row
         }
     const int i_new = (i + 1 == W) ? 0 : i + 1;
     if (i_new == 0) full = 1;
@@ -493,9 +533,11 @@ __device__ __forceinline__ void env_compute_rows(const StepParams& p, int e, int
     const float epr = __fadd_rn(sc.epr, r);
     if (lane == 0) {
         p.reward[e] = r; p.done[e] = (uint8_t)dn;
-        if (p.reward_host) { p.reward_host[e] = r; p.done_host[e] = (uint8_t)dn; }   // mapped pinned host memory: posted PCIe writes
-        if (p.value_sink) p.value_sink[e] = Vn;                  // RolloutBuffer.v[slot] (on_policy.py:65)
-        if (p.index_sink) p.index_sink[e] = sc.t0e + k_new;      // loader item of this step (off_policy.py:87 → buffer.py:34)
+        if (!NOSINKS) {
+            if (p.reward_host) { p.reward_host[e] = r; p.done_host[e] = (uint8_t)dn; }   // mapped pinned host memory: posted PCIe writes
+            if (p.value_sink) p.value_sink[e] = Vn;              // RolloutBuffer.v[slot] (on_policy.py:65)
+            if (p.index_sink) p.index_sink[e] = sc.t0e + k_new;  // loader item of this step (off_policy.py:87 → buffer.py:34)
+        }
         if (STORE_STATE) {
             p.value[e] = Vn;
             p.idx[e] = i_new; p.is_full[e] = (uint8_t)full; p.t[e] = k_new;

@@ -96,7 +96,7 @@ def tuning():
     yield _lib
     for k in (_lib.TUNE_GROUP_ENVS, _lib.TUNE_CTAS_PER_SM):
         _lib.set_tuning(k, 0)
-    for k in (_lib.TUNE_FUSED, _lib.TUNE_RING_TMA, _lib.TUNE_FAST_FILL):
+    for k in (_lib.TUNE_FUSED, _lib.TUNE_RING_TMA, _lib.TUNE_FAST_FILL, _lib.TUNE_STAGED):
         _lib.set_tuning(k, 1)
 
 
@@ -462,6 +462,40 @@ def test_wide_asset_counts(A, tuning):
         np.testing.assert_array_equal(done.cpu().numpy(), d_o)
     compare_state(gpu, ora, "end")
     compare_obs(gpu.observe(), ora, "end")
+
+
+@pytest.mark.parametrize("commission", [0.0, 0.0025])
+@pytest.mark.parametrize("A,E,shape", [(132, 300, 0), (256, 2600, 0), (500, 300, 0), (500, 4000, 0), (1000, 150, 0), (1024, 2400, 0),
+                                       (500, 4000, 3), (500, 300, 3), (260, 3000, 3)])
+def test_staged_wide_env_kernel_vs_oracle_and_register_kernel(A, E, shape, commission, tuning):
+    """k_env_step_staged (rows staged one env ahead by TMA bulk copies, env_step_staged.cu) against the oracle, and bit for
+    bit against the register-load kernel k_env_step on the same inputs — table-driven and external-y, auto-resets included."""
+    W, L = 6, 9
+    tuning.set_tuning(tuning.TUNE_CTAS_PER_SM, shape)             # CTA shape / staging depth of the staged kernel
+    tuning.set_tuning(tuning.TUNE_STAGED, 2)                      # staged at any batch size
+    gpu, ora = make_pair(E, A, W, 5, episode_len=L, commission=commission)
+    tuning.set_tuning(tuning.TUNE_STAGED, 0)
+    ref, _ = make_pair(E, A, W, 5, episode_len=L, commission=commission)
+    g = torch.Generator().manual_seed(A + E)
+    gpu.reset(obs=False); ref.reset(obs=False)
+    n0 = tuning.load().pmrl_launch_count()
+    for s in range(2 * L + 3):
+        act = torch.randn(E, A, generator=g)
+        if s % 5 == 2:
+            act = torch.softmax(act, dim=1)
+        y = (1 + 0.01 * torch.randn(E, A, generator=g)).cuda() if s % 4 == 3 else None      # external price relatives
+        a = act.cuda()
+        tuning.set_tuning(tuning.TUNE_STAGED, 2)
+        _, r, done = gpu.step(a, y=y, obs=False)
+        tuning.set_tuning(tuning.TUNE_STAGED, 0)
+        _, r2, done2 = ref.step(a, y=y, obs=False)
+        assert torch.equal(r, r2) and torch.equal(done, done2), f"step {s}"
+        assert torch.equal(gpu.value, ref.value) and torch.equal(gpu.hist, ref.hist) and torch.equal(gpu.idx, ref.idx)
+        r_o, d_o = ora.step(act.numpy(), y.cpu().numpy() if y is not None else None)
+        np.testing.assert_array_equal(done.cpu().numpy(), d_o)
+        util.assert_rewards_close(r.cpu().numpy(), r_o, f"step {s}")
+    compare_state(gpu, ora, "end")
+    assert tuning.load().pmrl_launch_count() - n0 == 2 * (2 * L + 3)
 
 
 def test_graphed_step_matches_eager():
