@@ -31,10 +31,27 @@ constexpr int kRtGroup = kRtWarps;                 // envs per group, one per wa
 constexpr int kRtGroupNarrow = 2 * kRtWarps;       // A <= 64: two envs per warp
 
 struct RtEnv { int row0, shift, fresh_slot, pad; };
-struct RtFeat { float4 fv[4][2]; };
 
-template <int NPL, bool HASC, int VEC, int WT>
+// Tile geometry for C4 = (F - 1) / 4 float4 chunks per (asset, table row): F = 5, 9, 13, 17 (OHLC, OHLC + indicator outputs).
+// A warp owns RPW asset rows of a tile and stages ≤ 8 float4 per thread one tile ahead, so wider rows mean lower tiles:
+// 32 rows at F = 5 (32 KB at W = 50), 16 at F = 9 (28.8 KB), 8 at F = 13 / 17.
+template <int C4> struct RtGeom {
+    static constexpr int F = 4 * C4 + 1;
+    static constexpr int RPW = C4 == 1 ? 4 : C4 == 2 ? 2 : 1;      // asset rows per warp and tile
+    static constexpr int TR = 8 * RPW;                             // asset rows per tile
+    static constexpr int NSUB = 32 / TR;                           // lane groups sharing the weight channel of a tile row
+    static constexpr int JMAX = 8 / NSUB;                          // window slots (stride 8) per lane, W <= 64
+};
+template <int C4, int WT> struct RtFeat {
+    static constexpr int MW = WT ? (WT * C4 + 31) / 32 : 2 * C4;   // float4 chunks of one window run per lane (W <= 64)
+    float4 fv[RtGeom<C4>::RPW][MW];
+};
+
+template <int NPL, bool HASC, int VEC, int WT, int C4>
 __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepParams p) {
+    using Geo = RtGeom<C4>;
+    using Feat = RtFeat<C4, WT>;
+    constexpr int F = Geo::F, RPW = Geo::RPW, TR = Geo::TR, NSUB = Geo::NSUB, JMAX = Geo::JMAX, MW = Feat::MW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_stats[kRtWarps * PMRL_STATS_LEN];
     __shared__ RtEnv s_env[kRtGroupNarrow];
@@ -43,25 +60,28 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
     const int W = WT ? WT : p.W;
     const int A = p.A, T = p.T, G = p.group_envs;
     const int WA = W * A;
-    const int tile_floats = 32 * W * 5;
+    const int tile_floats = TR * W * F;
     float* const tile0 = reinterpret_cast<float*>(smem_raw);
     float* const tile1 = tile0 + tile_floats;
-    float* const s_ring = tile1 + tile_floats;                       // [2][W*A] rings of two consecutive envs
+    float* const s_ring = tile1 + tile_floats;                       // [NB][W*A] rings of consecutive envs
     const int NB = p.ring_bufs;                                      // rings resident at once (2 at A = 100, up to 4 for narrow envs)
     float* const s_wnew = s_ring + NB * WA;                          // [G*A]    w' per asset-row of the group
     int* const s_ea = reinterpret_cast<int*>(s_wnew + G * A);        // [G*A]    (env-in-group << 16) | asset
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_groups = (p.E + G - 1) / G;
-    const size_t row_floats = (size_t)W * 5;
+    const size_t row_floats = (size_t)W * F;
     if (tid == 0) { for (int b = 0; b < 4; ++b) mbar_init(&s_rbar[b], 1); mbar_fence_init(); }
     WarpStats ws;
     wstats_init(ws);
     __syncthreads();
 
-    const int fbase = (warp * W + lane) * 5, fstep = 8 * W * 5;
-    const bool w0 = lane < W, w1 = lane + 32 < W;
-    const int wbase = (lane * W + warp) * 5 + 4;
-    const int nj = min(8, max(0, (W - warp + 7) >> 3));
+    // feature window of one asset = NCH = W·C4 contiguous float4 chunks of the table; lane l stages chunks l, l + 32, …
+    // and scatters chunk k to tile offset (k / C4)·F + 4·(k % C4) of its asset row
+    const int NCH = W * C4;
+    const int rl = lane % TR, sub = lane / TR;                       // weight channel: tile row of this lane, its window-slot phase
+    const int wbase = (rl * W + warp + 8 * sub) * F + (F - 1);
+    const int n8 = max(0, (W - warp + 7) >> 3);                      // window slots warp, warp + 8, … below W
+    const int nj = n8 > sub ? (n8 - sub + NSUB - 1) / NSUB : 0;
     const float4* __restrict__ tbl = reinterpret_cast<const float4*>(p.feat_am) + lane;
 
     int buf = 0;
@@ -126,7 +146,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
         }
         // ---------------- phase 2 ----------------
         const int R = ne * A;
-        const int ntiles = (R + 31) >> 5, nfull = R >> 5;
+        const int ntiles = (R + TR - 1) / TR, nfull = R / TR;
         const float* __restrict__ hist_g = p.hist + (size_t)e0 * WA;
         float* const obs_grp = p.obs + (size_t)e0 * A * row_floats;
         int issued = 0;                                               // envs of this group whose ring load has been issued
@@ -139,77 +159,85 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
             }
         };
         if (tid == 0) issue_rings(min(ne, NB));
-        int wel = lane / A, wa = lane - wel * A;                      // (env-in-group, asset) of this lane's weight row
+        int wel = rl / A, wa = rl - wel * A;                          // (env-in-group, asset) of this lane's weight row
 
-        auto load_feat = [&](RtFeat& fr, int r0, auto partial) {
+        auto load_feat = [&](Feat& fr, int r0, auto partial) {
             constexpr bool PARTIAL = decltype(partial)::value;
-            const int nr = PARTIAL ? R - r0 : 32;
+            const int nr = PARTIAL ? R - r0 : TR;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < RPW; ++i) {
                 if (!PARTIAL || warp + 8 * i < nr) {
                     const int ea = s_ea[r0 + warp + 8 * i];
-                    const float4* __restrict__ src = tbl + ((ea & 0xffff) * T + s_env[ea >> 16].row0);
-                    if (w0) fr.fv[i][0] = ld_keep4(src, kPolicyEvictLast);
-                    if (w1) fr.fv[i][1] = ld_keep4(src + 32, kPolicyEvictLast);
+                    const float4* __restrict__ src = tbl + (size_t)((ea & 0xffff) * T + s_env[ea >> 16].row0) * C4;
+#pragma unroll
+                    for (int m = 0; m < MW; ++m)
+                        if (lane + 32 * m < NCH) fr.fv[i][m] = ld_keep4(src + 32 * m, kPolicyEvictLast);
                 }
             }
         };
-        auto spill_tile = [&](const RtFeat& fr, float* __restrict__ tile, int r0, auto partial) {
+        auto spill_tile = [&](const Feat& fr, float* __restrict__ tile, int r0, auto partial) {
             constexpr bool PARTIAL = decltype(partial)::value;
-            const int nr = PARTIAL ? R - r0 : 32;
+            const int nr = PARTIAL ? R - r0 : TR;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < RPW; ++i) {
                 if (!PARTIAL || warp + 8 * i < nr) {
-                    float* d = tile + fbase + i * fstep;
-                    if (w0) { const float4 v = fr.fv[i][0]; d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
-                    if (w1) { const float4 v = fr.fv[i][1]; d[160] = v.x; d[161] = v.y; d[162] = v.z; d[163] = v.w; }
+                    float* drow = tile + (warp + 8 * i) * W * F;
+#pragma unroll
+                    for (int m = 0; m < MW; ++m) {
+                        const int k = lane + 32 * m;
+                        if (k < NCH) {
+                            float* d = drow + (k / C4) * F + 4 * (k % C4);
+                            const float4 v = fr.fv[i][m];
+                            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                        }
+                    }
                 }
             }
-            if (!PARTIAL || lane < nr) {                              // weight channel straight from the staged ring
+            if (!PARTIAL || rl < nr) {                                // weight channel straight from the staged ring
                 const int n = ebase + wel;
                 const int b = n % NB;
                 mbar_wait(&s_rbar[b], (uint32_t)((n / NB) & 1));
                 const RtEnv ge = s_env[wel];
                 const float* __restrict__ rs = s_ring + b * WA + wa;
-                const float fresh = s_wnew[r0 + lane];
+                const float fresh = s_wnew[r0 + rl];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < JMAX; ++j) {
                     if (j < nj) {
-                        const int slot = warp + 8 * j - ge.shift;
+                        const int slot = warp + 8 * (j * NSUB + sub) - ge.shift;
                         float v = 0.0f;                               // zero front padding while the ring is not full
                         if (slot >= 0) v = (slot == ge.fresh_slot) ? fresh : rs[slot * A];
-                        tile[wbase + 40 * j] = v;
+                        tile[wbase + 8 * NSUB * F * j] = v;
                     }
                 }
             }
-            wa += 32;
+            wa += TR;
             while (wa >= A) { wa -= A; ++wel; }
         };
 
-        RtFeat fr;
+        Feat fr;
         if (nfull > 0) load_feat(fr, 0, std::false_type{}); else load_feat(fr, 0, std::true_type{});
         for (int ti = 0; ti < ntiles; ++ti) {
             float* const tile = buf ? tile1 : tile0;
             if (tid == 0) bulk_wait_read<1>();                        // the store that last used this buffer has drained
             __syncthreads();
-            const int r0 = ti * 32;
+            const int r0 = ti * TR;
             if (ti < nfull) spill_tile(fr, tile, r0, std::false_type{}); else spill_tile(fr, tile, r0, std::true_type{});
             if (ti + 1 < ntiles) {
-                if (ti + 1 < nfull) load_feat(fr, r0 + 32, std::false_type{}); else load_feat(fr, r0 + 32, std::true_type{});
+                if (ti + 1 < nfull) load_feat(fr, r0 + TR, std::false_type{}); else load_feat(fr, r0 + TR, std::true_type{});
             }
             fence_proxy_async_smem();
             __syncthreads();
-            const int nr = min(32, R - r0);
+            const int nr = min(TR, R - r0);
             float* const gdst = obs_grp + (size_t)r0 * row_floats;
-            const int n = nr * W * 5;
+            const int n = nr * W * F;
             if (((((uintptr_t)gdst) | ((size_t)n * 4)) & 15) == 0) {
                 if (tid == 0) { bulk_store_s2g(gdst, tile, (uint32_t)n * 4u, kPolicyEvictFirst); bulk_commit(); }
             } else {
                 for (int q = tid; q < n; q += kRtThreads) gdst[q] = tile[q];
             }
-            // envs below (r0+32)/A are complete (every thread passed the barrier after its last read of their ring):
-            // their buffers can take the rings of the envs two positions further on
-            if (tid == 0) issue_rings(min(ne, (r0 + 32) / A + NB));
+            // envs below (r0+TR)/A are complete (every thread passed the barrier after its last read of their ring):
+            // their buffers can take the rings of the envs NB positions further on
+            if (tid == 0) issue_rings(min(ne, (r0 + TR) / A + NB));
             buf ^= 1;
         }
         ebase += ne;
@@ -230,25 +258,25 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
 
 using namespace pmrl;
 
-template <int NPL, bool HASC, int VEC, int WT>
+template <int NPL, bool HASC, int VEC, int WT, int C4>
 static int launch_rt_t(StepParams& p, size_t smem, int grid, cudaStream_t s) {
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs_rt<NPL, HASC, VEC, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs_rt<NPL, HASC, VEC, WT, C4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return pmrl_fail((int)e, "cudaFuncSetAttribute(k_env_step_obs_rt) failed");
         attr_done[dev] = true;
     }
-    k_env_step_obs_rt<NPL, HASC, VEC, WT><<<grid, kRtThreads, smem, s>>>(p);
+    k_env_step_obs_rt<NPL, HASC, VEC, WT, C4><<<grid, kRtThreads, smem, s>>>(p);
     return pmrl_check_launch("k_env_step_obs_rt");
 }
 
-template <int NPL, int VEC>
+template <int NPL, int VEC, int C4>
 static int launch_rt_w(StepParams& p, size_t smem, int grid, cudaStream_t s) {
     const bool hasc = p.commission > 0.0f;
-    if (p.W == 50) return hasc ? launch_rt_t<NPL, true, VEC, 50>(p, smem, grid, s) : launch_rt_t<NPL, false, VEC, 50>(p, smem, grid, s);
-    return hasc ? launch_rt_t<NPL, true, VEC, 0>(p, smem, grid, s) : launch_rt_t<NPL, false, VEC, 0>(p, smem, grid, s);
+    if (p.W == 50) return hasc ? launch_rt_t<NPL, true, VEC, 50, C4>(p, smem, grid, s) : launch_rt_t<NPL, false, VEC, 50, C4>(p, smem, grid, s);
+    return hasc ? launch_rt_t<NPL, true, VEC, 0, C4>(p, smem, grid, s) : launch_rt_t<NPL, false, VEC, 0, C4>(p, smem, grid, s);
 }
 
 // Envs per group for a batch of E envs on `slots` persistent CTAs.  A CTA's time is (rounds it runs) x (envs per group +
@@ -269,29 +297,37 @@ static int pick_group(int E, int slots, int gmax) {
 }
 
 int pmrl_launch_step_obs_rt(StepParams& p, int npl, int vec, int group, int ctas_per_sm, cudaStream_t s) {
-    if (p.F != 5 || p.W > 64 || npl > 4 || p.A < 32) return -100;     // A >= 32: a 32-row tile spans at most two envs
+    // F = 5, 9, 13, 17: four feature channels per float4 chunk of the asset-major table (OHLC, OHLC + indicator outputs)
+    if (p.F < 5 || p.F > 17 || (p.F - 1) % 4 != 0 || ((uintptr_t)p.feat_am) % 16 != 0) return -100;
+    const int c4 = (p.F - 1) / 4;
+    if (p.W > 64 || npl > 4 || p.A < 32) return -100;                 // A >= 32: a tile spans at most two envs
     if (((size_t)p.W * p.A) % 4 != 0 || ((uintptr_t)p.hist) % 16 != 0) return -100;   // every env's ring 16-byte aligned
-    if ((size_t)p.A * p.T >= (1u << 31) || p.A >= 65536) return -100;
+    if ((size_t)p.A * p.T * c4 >= (1u << 31) || p.A >= 65536) return -100;
     const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : 2;
     const int slots = pmrl_sm_count() * per_sm;
     const int gmax = npl <= 2 ? kRtGroupNarrow : kRtGroup;
     int G = group > 0 ? group : pick_group(p.E, slots, gmax);
     if (G > gmax) G = gmax;
     p.group_envs = G;
-    p.tile_assets = 32;
-    // ring buffers: a 32-row tile may touch two envs, and the ring of env n+NB can only be requested once env n is
+    const int tr = c4 == 1 ? 32 : c4 == 2 ? 16 : 8;
+    p.tile_assets = tr;
+    // ring buffers: a tile may touch two envs, and the ring of env n+NB can only be requested once env n is
     // done — with two buffers a 50-asset env gets its ring one tile (≈2 us) before it is needed, less than a DRAM round
     // trip under load.  Narrow envs have small rings: keep up to four resident.
     const size_t budget = (size_t)(226 * 1024) / per_sm - 1024;
-    const size_t fixed = (size_t)2 * 32 * p.W * 5 * 4 + (size_t)G * p.A * 8, ring_bytes = (size_t)p.W * p.A * 4;
+    const size_t fixed = (size_t)2 * tr * p.W * p.F * 4 + (size_t)G * p.A * 8, ring_bytes = (size_t)p.W * p.A * 4;
     if (fixed + 2 * ring_bytes > budget) return -100;
     int nb = (int)((budget - fixed) / ring_bytes);
     p.ring_bufs = nb > 4 ? 4 : nb;
     const size_t smem = fixed + (size_t)p.ring_bufs * ring_bytes;
     const int n_groups = (p.E + G - 1) / G;
     const int grid = n_groups < slots ? n_groups : slots;
-#define RT_CASE(N, V) if (npl == N && vec == V) return launch_rt_w<N, V>(p, smem, grid, s)
-    RT_CASE(1, 1); RT_CASE(2, 1); RT_CASE(2, 2); RT_CASE(4, 1); RT_CASE(4, 2); RT_CASE(4, 4);
+#define RT_CASE(N, V, C) if (npl == N && vec == V && c4 == C) return launch_rt_w<N, V, C>(p, smem, grid, s)
+    RT_CASE(1, 1, 1); RT_CASE(2, 1, 1); RT_CASE(2, 2, 1); RT_CASE(4, 1, 1); RT_CASE(4, 2, 1); RT_CASE(4, 4, 1);
+    // wider feature sets: the even / 16-byte asset maps only (odd asset counts take the two-kernel path)
+    RT_CASE(2, 2, 2); RT_CASE(4, 2, 2); RT_CASE(4, 4, 2);
+    RT_CASE(2, 2, 3); RT_CASE(4, 2, 3); RT_CASE(4, 4, 3);
+    RT_CASE(2, 2, 4); RT_CASE(4, 2, 4); RT_CASE(4, 4, 4);
 #undef RT_CASE
     return -100;
 }

@@ -29,12 +29,22 @@ __device__ __forceinline__ void obs_tile_fill_features(const StepParams& p, floa
             d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         }
     } else {
+        // any channel count: a warp owns an asset row of the tile (its window is ONE contiguous run of W·(F-1) floats in
+        // the asset-major table), lanes walk the run 32 floats at a time — coalesced 128-byte loads — and carry their
+        // (window row, channel) position incrementally: no integer division per element.
         const int per_asset = W * Fm1;
-        const int n = na * per_asset;
-        for (int q = tid; q < n; q += nthreads) {
-            const int al = q / per_asset, rem = q - al * per_asset;
-            const int w = rem / Fm1, c = rem - w * Fm1;
-            tile[(al * W + w) * F + c] = ld_keep(p.feat_am + ((size_t)(a0 + al) * T + row0) * Fm1 + rem, pol_keep);
+        const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+        const int dq = 32 / Fm1, dr = 32 - dq * Fm1;               // a stride of 32 floats = dq rows + dr channels
+        const int w_first = lane / Fm1, c_first = lane - w_first * Fm1;
+        for (int al = warp; al < na; al += nwarps) {
+            const float* __restrict__ src = p.feat_am + ((size_t)(a0 + al) * T + row0) * Fm1;
+            float* __restrict__ drow = tile + al * W * F;
+            int w = w_first, c = c_first;
+            for (int rem = lane; rem < per_asset; rem += 32) {
+                drow[w * F + c] = ld_keep(src + rem, pol_keep);
+                w += dq; c += dr;
+                if (c >= Fm1) { c -= Fm1; ++w; }
+            }
         }
     }
 }
@@ -48,13 +58,14 @@ __device__ __forceinline__ void obs_tile_fill_weights(const StepParams& p, float
                                                       int tid, int nthreads) {
     const int W = p.W, F = p.F, A = p.A;
     const int shift = is_full ? 0 : (W - idx);      // column w shows ring slot w - shift (weight_buffer.py:38-42)
-    const int n = W * na;
-    for (int q = tid; q < n; q += nthreads) {
-        const int w = q / na, al = q - w * na;      // asset fastest → coalesced ring-row reads
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    for (int w = warp; w < W; w += nwarps) {          // lanes over assets → coalesced ring-row reads, no division per element
         const int slot = w - shift;
-        float v = 0.0f;
-        if (slot >= 0) v = (slot == fresh_slot) ? fresh[a0 + al] : ld_stream(hist_e + (size_t)slot * A + a0 + al);
-        tile[(al * W + w) * F + (F - 1)] = v;
+        for (int al = lane; al < na; al += 32) {
+            float v = 0.0f;
+            if (slot >= 0) v = (slot == fresh_slot) ? fresh[a0 + al] : ld_stream(hist_e + (size_t)slot * A + a0 + al);
+            tile[(al * W + w) * F + (F - 1)] = v;
+        }
     }
 }
 

@@ -90,21 +90,51 @@ def pack_tables(series=None, close=None, num_assets: int = 0, channels: int = 0)
     return feat_am, close_tm
 
 
-def build_env_tables(ohlc, d=0.4, thres: float = 1e-5, scaler: str | None = "minmax", close_channel: int = 3):
-    """The reference pipeline FFD → scale → window layout (data/data_loader.py:37-43) for an OHLC table [T, A, C]:
-    every (asset, channel) series is fractionally differenced with `d` (scalar, [C] or [A, C]), scaled over the
-    whole split, and packed to feat_am [A, T', C]; the raw close plane (for y_t) is row-aligned to it → close_tm [T', A].
-    Returns dict(feat_am, close_tm, max_width, rows)."""
+def build_env_tables(ohlc, d=0.4, thres: float = 1e-5, scaler: str | None = "minmax", close_channel: int = 3,
+                     indicators=None, d_indicators=None, feature_channels: int = 4):
+    """The reference pipeline indicators → FFD → scale → window layout (data/data_loader.py:37-43) for an OHLC(V) table
+    [T, A, C]:
+
+      1. `indicators` (config.base.INDICATORS form, see `add_indicators`): the indicator windows are computed from the raw
+         table and appended as feature channels; every series is clipped by the largest lookback (instrument.py:207-232);
+      2. every (asset, channel) series is fractionally differenced — the first `feature_channels` table channels with `d`
+         (scalar, [C'] or [A, C']), the indicator outputs with `d_indicators` (scalar or one value per output; default: `d`
+         when scalar, else 0) — except the features data/ffd.py:21 ignores BY NAME (the reference compares the full feature
+         name, so 'volume' is ignored while a suffixed indicator name such as 'rsi_30' is differenced like any other);
+      3. scaled over the whole split (instrument.py:318-336) and packed to feat_am [A, T', F-1]; the raw close plane (for
+         y_t) is row-aligned to it → close_tm [T', A].
+
+    F - 1 = feature_channels + n_out: with F - 1 a multiple of four (OHLC + ema + bbands → F = 9) the fused step+obs kernel
+    consumes the table directly.  Returns dict(feat_am, close_tm, max_width, lookback, rows, widths, names)."""
     tbl = _cuda_f32(ohlc)
     T, A, C = tbl.shape
-    dd = np.broadcast_to(np.asarray(d, np.float64), (A, C)).reshape(-1)
-    series = tbl.permute(1, 2, 0).contiguous().view(A * C, T)          # [A*C, T] series-major (one-time setup copy)
-    out, widths, mw = ffd_transform(series, dd, thres)
+    Cf = min(int(feature_channels), C)
+    base_names = ["open", "high", "low", "close", "volume"][:Cf] if Cf <= 5 else [f"ch{i}" for i in range(Cf)]
+    names, lb, n_out = list(base_names), 0, 0
+    series = tbl[:, :, :Cf].permute(1, 2, 0).contiguous()                # [A, Cf, T] series-major (one-time setup copy)
+    if indicators:
+        ind_names, ind, lb = add_indicators(tbl, indicators)               # [A, n_out, T - lb]
+        n_out = ind.shape[1]
+        names += ind_names
+        series = torch.cat([series[:, :, lb:], ind], dim=1).contiguous()    # [A, Cf + n_out, T - lb]
+    Ct = Cf + n_out
+    Tl = T - lb
+    dd = np.zeros((A, Ct), np.float64)
+    dd[:, :Cf] = np.broadcast_to(np.asarray(d, np.float64), (A, Cf))
+    if n_out:
+        if d_indicators is None:
+            d_indicators = float(d) if np.ndim(d) == 0 else 0.0
+        dd[:, Cf:] = np.broadcast_to(np.asarray(d_indicators, np.float64), (A, n_out))
+    for c, name in enumerate(names):
+        if name in FEAT_IGNORE:
+            dd[:, c] = 0.0
+    out, widths, mw = ffd_transform(series.view(A * Ct, Tl), dd.reshape(-1), thres)
     if scaler is not None:
         out = scale_series(out, scaler, out=out)
-    close = tbl[mw:, :, close_channel].t().contiguous()                 # [A, T']
-    feat_am, close_tm = pack_tables(out, close, num_assets=A, channels=C)
-    return {"feat_am": feat_am, "close_tm": close_tm, "max_width": mw, "rows": T - mw, "widths": widths}
+    close = tbl[lb + mw:, :, close_channel].t().contiguous()             # [A, T']
+    feat_am, close_tm = pack_tables(out, close, num_assets=A, channels=Ct)
+    return {"feat_am": feat_am, "close_tm": close_tm, "max_width": mw, "lookback": lb, "rows": Tl - mw, "widths": widths,
+            "names": names}
 
 
 class FixedFracDiff:

@@ -395,6 +395,54 @@ def test_indicator_windows_vs_oracle():
         features.add_indicators(tbl, {"sar": {}})
 
 
+def test_build_env_tables_with_indicators_feeds_the_fused_kernel():
+    """N3 → a10 → a11 → table: indicator windows appended as features (config/base.py:30-44), FFD'ed, scaled and packed to an
+    F = 9 table (OHLC + ema + bbands + weight slot) that the fused step+obs kernel consumes; every stage against its oracle."""
+    import pmrl_b200
+    from oracle import indicators_oracle as io
+    from oracle.env_oracle import OracleEnv
+    from pmrl_b200 import features, synth, _lib
+    from pmrl_b200.env import BatchedTradingEnv
+    T, A, W, L, E = 900, 36, 12, 30, 40
+    tbl = synth.gbm_ohlc(T, A, seed=5)
+    inds = [("ema", {"timeperiod": 30}), ("bbands", {"timeperiod": 20})]
+    t = features.build_env_tables(tbl, d=0.6, thres=1e-4, scaler="minmax", indicators=inds)
+    lb, mw = t["lookback"], t["max_width"]
+    assert lb == 29 and t["names"] == ["open", "high", "low", "close", "ema_30", "upperband_20", "middleband_20", "lowerband_20"]
+    assert t["feat_am"].shape == (A, T - lb - mw, 8) and t["rows"] == T - lb - mw
+    c = tbl[:, :, 3].numpy().T
+    series = np.empty((A, 8, T - lb), np.float32)
+    series[:, :4] = tbl.permute(1, 2, 0).numpy()[:, :, lb:]
+    for a in range(A):
+        series[a, 4] = io.ema(c[a], 30)[lb:]
+        series[a, 5], series[a, 6], series[a, 7] = (x[lb:] for x in io.bbands(c[a], 20))
+    want, _, mw_o = ffd_oracle.ffd_transform(series.reshape(A * 8, T - lb), np.full(A * 8, 0.6), 1e-4)
+    assert mw == mw_o
+    want = ffd_oracle.scale_series(want, "minmax").reshape(A, 8, T - lb - mw).transpose(0, 2, 1)
+    np.testing.assert_allclose(t["feat_am"].cpu().numpy(), want, rtol=1e-4, atol=5e-5)
+    np.testing.assert_array_equal(t["close_tm"].cpu().numpy(), tbl[lb + mw:, :, 3].numpy())
+    # the env steps on the packed F = 9 table through ONE fused launch per step
+    rows = t["rows"]
+    t0 = synth.episode_offsets(E, rows, W, L)
+    cfg = pmrl_b200.EnvConfig(num_envs=E, num_assets=A, window_size=W, num_features=9, episode_len=L)
+    env = BatchedTradingEnv.from_tables(cfg, t["close_tm"], t["feat_am"], t0=t0)
+    feat_tm = t["feat_am"].permute(1, 0, 2).contiguous().cpu().numpy()
+    ora = OracleEnv(E, A, W, 9, close=t["close_tm"].cpu().numpy(), feat=feat_tm, t0=t0.numpy(), episode_len=L)
+    compare = lambda obs, msg: (np.testing.assert_array_equal(obs.cpu().numpy()[..., :8], ora.obs()[..., :8], err_msg=msg),
+                                np.testing.assert_allclose(obs.cpu().numpy()[..., 8], ora.obs()[..., 8], rtol=1e-5, atol=1e-6, err_msg=msg))
+    compare(env.reset(), "reset")
+    g = torch.Generator().manual_seed(3)
+    n0 = _lib.load().pmrl_launch_count()
+    for s in range(L + 4):
+        act = torch.randn(E, A, generator=g)
+        obs, r, done = env.step(act.cuda())
+        r_o, d_o = ora.step(act.numpy())
+        np.testing.assert_array_equal(done.cpu().numpy(), d_o)
+        np.testing.assert_allclose(r.cpu().numpy(), r_o, rtol=1e-5, atol=1e-6)
+        compare(obs, f"step {s}")
+    assert _lib.load().pmrl_launch_count() - n0 == L + 4              # fused: one kernel per step
+
+
 def test_directional_movement_indicators_vs_oracle():
     """adx / dx of the reference's commented default set (config/base.py:38-39)."""
     from oracle import indicators_oracle as io
