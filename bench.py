@@ -373,12 +373,15 @@ def measure_e2e(ctx, env, pool, E, A, obs, steps, chunks=0):
             "ms_per_step": ems / steps}
 
 
-def kernel_name(obs, launches_per_step, A, F, burst=0):
+def kernel_name(obs, launches_per_step, A, F, burst=0, E=1 << 30):
+    """Name of the dominant kernel of a workload (what `roofline` is about), from the launcher's own dispatch rules."""
+    staged = A > 128 and A % 4 == 0 and E > 148 * 2 * 8            # env_kernels.cu:launch_step_s
+    state = "k_env_step_staged" if staged else "k_env_step"
     if burst:
-        return "k_env_step_burst"
+        return f"{state} x{burst} launches" if staged else "k_env_step_burst"
     if not obs:
-        return "k_env_step"
-    return "k_env_step_obs_rt" if launches_per_step <= 1.001 else "k_env_step + k_obs_build_rows"
+        return state
+    return "k_env_step_obs_rt" if launches_per_step <= 1.001 else f"{state} + k_obs_build_rows"
 
 
 def config_entry(ctx, name, steps, warmup, mode="step", K=0, e2e=True, flushed=False):
@@ -428,7 +431,7 @@ def config_entry(ctx, name, steps, warmup, mode="step", K=0, e2e=True, flushed=F
            "ms_per_step": ms / steps, "value": value, "unit": "asset-steps/s", "env_steps_per_s": value / A,
            "gpu_launches": launches,
            "roofline": roofline_entry(ctx, value, ctx.world, bpa, E, A, name if mode == "step" else f"{name}_{mode}",
-                                      kernel_name(obs, launches / steps, A, F, burst=(mode == "burst"))),
+                                      kernel_name(obs, launches / steps, A, F, burst=(K if mode == "burst" else 0), E=E)),
            "l2": "working set > L2" if E * A * 4 * (W if obs else 2) > L2_BYTES else "L2-resident back to back"}
     if flushed:
         fms = ctx.timed_flushed(fn, steps, warmup + steps)
@@ -727,7 +730,7 @@ def main():
             "env_steps_per_s": value / A,
             "config": cfg_line,
             "roofline": roofline_entry(ctx, value, world, bpa, E, A, args.workload,
-                                       kernel_name(obs, gpu_launches / args.steps, A, F, burst=bool(args.burst))),
+                                       kernel_name(obs, gpu_launches / args.steps, A, F, burst=args.burst, E=E)),
             "clocks": clocks,
             "gpu_launches": gpu_launches,
             "stats": {k: stats[k] for k in ("n_envs", "mean_reward", "mean_value", "n_done")},

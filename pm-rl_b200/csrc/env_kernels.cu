@@ -122,10 +122,10 @@ __global__ void __launch_bounds__(kStepThreads, kStepMinBlocks<NPL, HASC, false>
             if constexpr (!REGPF) {
                 if (k > 0) { float none[1]; env_load_rows<NPL, false, VEC, TAIL, false, LOADY>(q, e, lane, sc, a, yv, none); }
             }
-            env_compute_rows<NPL, HASC, VEC, TAIL, LOADY, false>(q, e, lane, sc, a, yv, wl, so, ws);
+            // (pmrl_env_step_burst takes no sinks / host mirrors: their per-step null tests are compiled out)
+            env_compute_rows<NPL, HASC, VEC, TAIL, LOADY, false, false, NoHook, false, /*NOSINKS=*/true>(q, e, lane, sc, a, yv, wl, so, ws);
             sc.V = so.V; sc.i = so.idx_new; sc.full = so.is_full; sc.k = so.k; sc.epr = so.epr;
             q.actions += EA; q.reward += p.E; q.done += p.E;
-            if (q.reward_host) { q.reward_host += p.E; q.done_host += p.E; }
             if constexpr (REGPF) {                        // narrow envs: the prefetched rows move into the row that is now dead
                 if (k + 1 < K) {
 #pragma unroll
@@ -578,5 +578,19 @@ extern "C" int pmrl_env_step_burst(const PmrlEnvCfg* cfg, const PmrlTables* tbl,
     if (int rc = prepare_step(cfg, tbl, st, &io, p)) return rc;
     p.burst = K;
     const int npl = env_npl_for(p.A), vec = vec_for_pointers(p, npl);
+    if (g_tune_staged && npl >= 8 && (g_tune_staged == 2 || (p.E + kStepWarps - 1) / kStepWarps > pmrl_sm_count() * 2)) {
+        // wide envs, large batches: the single-step kernel with its rows staged by TMA bulk copies is faster per step than
+        // the register-resident burst (config 5: 0.335 vs 0.365 ms) and launch latency is negligible at this size, so the
+        // burst is K of those launches enqueued here — the same arithmetic, bit-identical results
+        p.burst = 0;
+        const size_t EA = (size_t)p.E * p.A;
+        for (int k = 0; k < K; ++k) {
+            const int rc = pmrl_launch_step_staged(p, npl, vec, g_tune_ctas_per_sm, (cudaStream_t)stream);
+            if (rc == -100) { if (k == 0) { p.burst = K; return launch_step_burst(p, npl, vec, (cudaStream_t)stream); } return pmrl_fail(PMRL_E_ARG, "env_step_burst: staged launch refused mid-burst"); }
+            if (rc != 0) return rc;
+            p.actions += EA; p.reward += p.E; p.done += p.E;
+        }
+        return 0;
+    }
     return launch_step_burst(p, npl, vec, (cudaStream_t)stream);
 }

@@ -43,7 +43,7 @@ template <int C4> struct RtGeom {
     static constexpr int JMAX = 8 / NSUB;                          // window slots (stride 8) per lane, W <= 64
 };
 template <int C4, int WT> struct RtFeat {
-    static constexpr int MW = WT ? (WT * C4 + 31) / 32 : 2 * C4;   // float4 chunks of one window run per lane (W <= 64)
+    static constexpr int MW = ((WT ? WT : 64) + 31) / 32 * C4;     // float4 chunks of one window run per lane (W <= 64)
     float4 fv[RtGeom<C4>::RPW][MW];
 };
 
@@ -75,14 +75,15 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
     wstats_init(ws);
     __syncthreads();
 
-    // feature window of one asset = NCH = W·C4 contiguous float4 chunks of the table; lane l stages chunks l, l + 32, …
-    // and scatters chunk k to tile offset (k / C4)·F + 4·(k % C4) of its asset row
-    const int NCH = W * C4;
+    // feature window of one asset = W·C4 contiguous float4 chunks of the table; lane l stages the C4 chunks of window rows
+    // l and l + 32 and scatters chunk (w, q) to tile offset w·F + 4q of its asset row: with lanes over w the shared stores
+    // of one instruction hit banks (F·l + const) mod 32 — F is odd, so all 32 differ (lanes over consecutive chunks, the
+    // first version, gave two-way conflicts at F = 9: 312 conflicts per tile, mio_throttle 1.6 per issue)
     const int rl = lane % TR, sub = lane / TR;                       // weight channel: tile row of this lane, its window-slot phase
     const int wbase = (rl * W + warp + 8 * sub) * F + (F - 1);
     const int n8 = max(0, (W - warp + 7) >> 3);                      // window slots warp, warp + 8, … below W
     const int nj = n8 > sub ? (n8 - sub + NSUB - 1) / NSUB : 0;
-    const float4* __restrict__ tbl = reinterpret_cast<const float4*>(p.feat_am) + lane;
+    const float4* __restrict__ tbl = reinterpret_cast<const float4*>(p.feat_am) + lane * C4;
 
     int buf = 0;
     int ebase = 0;                                                   // envs streamed by this CTA so far (ring buffer / phase index)
@@ -170,8 +171,8 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
                     const int ea = s_ea[r0 + warp + 8 * i];
                     const float4* __restrict__ src = tbl + (size_t)((ea & 0xffff) * T + s_env[ea >> 16].row0) * C4;
 #pragma unroll
-                    for (int m = 0; m < MW; ++m)
-                        if (lane + 32 * m < NCH) fr.fv[i][m] = ld_keep4(src + 32 * m, kPolicyEvictLast);
+                    for (int m = 0; m < MW; ++m)                      // m = (m / C4)-th window row of this lane, chunk m % C4
+                        if (lane + 32 * (m / C4) < W) fr.fv[i][m] = ld_keep4(src + 32 * C4 * (m / C4) + (m % C4), kPolicyEvictLast);
                 }
             }
         };
@@ -184,9 +185,9 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
                     float* drow = tile + (warp + 8 * i) * W * F;
 #pragma unroll
                     for (int m = 0; m < MW; ++m) {
-                        const int k = lane + 32 * m;
-                        if (k < NCH) {
-                            float* d = drow + (k / C4) * F + 4 * (k % C4);
+                        const int w = lane + 32 * (m / C4);
+                        if (w < W) {
+                            float* d = drow + w * F + 4 * (m % C4);
                             const float4 v = fr.fv[i][m];
                             d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
                         }
