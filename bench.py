@@ -367,8 +367,9 @@ def measure_e2e(ctx, env, pool, E, A, obs, steps, chunks=0):
     ems = ctx.max_over_ranks(e0.elapsed_time(e1))
     return {"value": ctx.world * E * A * steps / (ems * 1e-3), "unit": "asset-steps/s",
             "h2d_bytes_per_step": E * A * 4, "d2h_bytes_per_step": E * 5, "chunks": chunks,
-            "transfer": ("zero-copy: the step kernel reads the pinned host actions over PCIe and writes reward/done into mapped pinned memory"
-                         if chunks == 0 else "sliced H2D/D2H copies overlapped with per-slice kernels"),
+            "transfer": ("streamed: one kernel launched at once, the copy engine brings the pinned action rows in chunk by chunk behind it "
+                         "(the kernel waits per chunk); reward/done written by the kernel into mapped pinned memory; batches under 2 MB of "
+                         "actions: zero-copy PCIe reads" if chunks == 0 else "sliced H2D/D2H copies overlapped with per-slice kernels"),
             "api": "BatchedTradingEnv.step_host -> C-ABI pmrl_env_step_host",
             "ms_per_step": ems / steps}
 
@@ -601,7 +602,7 @@ def main():
             os.sched_setaffinity(0, cores[ctx.local_rank * per:(ctx.local_rank + 1) * per])
     except Exception:
         pass
-    tune_keys = {"group": _lib.TUNE_GROUP_ENVS, "ctas": _lib.TUNE_CTAS_PER_SM, "fast": _lib.TUNE_FAST_FILL, "rt": _lib.TUNE_RING_TMA, "staged": _lib.TUNE_STAGED}
+    tune_keys = {"group": _lib.TUNE_GROUP_ENVS, "ctas": _lib.TUNE_CTAS_PER_SM, "fast": _lib.TUNE_FAST_FILL, "rt": _lib.TUNE_RING_TMA, "staged": _lib.TUNE_STAGED, "hoststream": _lib.TUNE_HOST_STREAM}
     for kv in args.tune:
         k, v = kv.split("=")
         _lib.set_tuning(tune_keys[k], int(v))

@@ -52,7 +52,8 @@
 extern "C" {
 #endif
 
-#define PMRL_ABI_VERSION 3   /* 3: PmrlEnvState.ticket, PmrlStepIO + pmrl_env_step_io, pmrl_env_step_burst, pmrl_rollout_gather_index */
+#define PMRL_ABI_VERSION 4   /* 3: PmrlEnvState.ticket, PmrlStepIO + pmrl_env_step_io, pmrl_env_step_burst, pmrl_rollout_gather_index;
+                                4: PmrlStepIO.actions_ready (action rows streamed in under the kernel) */
 
 /* error codes (negative) */
 #define PMRL_E_ARG        (-1)   /* null pointer / bad enum */
@@ -130,6 +131,14 @@ typedef struct PmrlStepIO {
      * the kernel writes reward / done there as well (posted PCIe writes), so a host caller needs no D2H copy */
     float*    reward_host;     /* [E] or NULL */
     uint8_t*  done_host;       /* [E] or NULL (set together with reward_host) */
+    /* optional: the action rows arrive WHILE the kernel runs (pmrl_env_step_host streams them in with the copy engine under the
+     * kernel): actions_ready[c] becomes == actions_ready_seq (a release by the writer: copy-engine stream order) once the rows
+     * of envs [c << actions_ready_shift, (c + 1) << actions_ready_shift) are in `actions`; a warp waits for its env's flag
+     * before it reads the row (bounded: a flag that never arrives traps instead of hanging the GPU).  NULL → all rows are in
+     * `actions` when the kernel starts. */
+    const uint32_t* actions_ready;
+    uint32_t  actions_ready_seq;
+    int32_t   actions_ready_shift;
 } PmrlStepIO;
 
 /* stats vector written by pmrl_env_step (accumulated with atomics; caller zeroes it) */
@@ -166,6 +175,11 @@ const char* pmrl_last_error(void);
                                      price-relative rows staged one env ahead through shared memory by TMA bulk copies
                                      (env_step_staged.cu) when a warp has more than one env; 2: also for small batches; 0: register loads +
                                      L2 prefetch (k_env_step) */
+#define PMRL_TUNE_HOST_STREAM 13  /* pmrl_env_step_host with page-locked actions: 1 (default) the copy engine streams the action rows
+                                     into device memory in chunks UNDER the kernel, which waits per chunk (PmrlStepIO.actions_ready) — for batches
+                                     of >= 2 MB of actions with the obs materialised (>= 128 MB state-only), others take the
+                                     zero-copy path; 2: streamed at any size;
+                                     0: zero-copy, the kernel reads the host buffer over PCIe itself */
 int pmrl_set_tuning(int32_t key, int32_t value);
 
 /* Kernels this library has launched in this process so far (every entry point counts its own launches; bench.py reports

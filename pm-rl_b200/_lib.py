@@ -35,7 +35,8 @@ class PmrlEnvState(C.Structure):
 class PmrlStepIO(C.Structure):
     _fields_ = [("actions", c_void_p), ("y_ext", c_void_p), ("reward", c_void_p), ("done", c_void_p), ("obs", c_void_p),
                 ("obs_mode", i32), ("stats", c_void_p), ("action_sink", c_void_p), ("value_sink", c_void_p),
-                ("weight_sink", c_void_p), ("index_sink", c_void_p), ("reward_host", c_void_p), ("done_host", c_void_p)]
+                ("weight_sink", c_void_p), ("index_sink", c_void_p), ("reward_host", c_void_p), ("done_host", c_void_p),
+                ("actions_ready", c_void_p), ("actions_ready_seq", C.c_uint32), ("actions_ready_shift", i32)]
 
 
 P = C.POINTER
@@ -105,7 +106,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here means header and library diverged
         fn.restype = res
         fn.argtypes = args
-    if lib.pmrl_abi_version() != 3:
+    if lib.pmrl_abi_version() != 4:
         raise PmrlError("libpmrl_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -137,7 +138,7 @@ def current_stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-TUNE_GROUP_ENVS, TUNE_CTAS_PER_SM, TUNE_FUSED, TUNE_FAST_FILL, TUNE_RING_TMA, TUNE_STAGED = 2, 3, 4, 5, 11, 12
+TUNE_GROUP_ENVS, TUNE_CTAS_PER_SM, TUNE_FUSED, TUNE_FAST_FILL, TUNE_RING_TMA, TUNE_STAGED, TUNE_HOST_STREAM = 2, 3, 4, 5, 11, 12, 13
 
 
 def set_tuning(key: int, value: int) -> None:

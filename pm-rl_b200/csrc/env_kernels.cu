@@ -416,6 +416,7 @@ extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
         case PMRL_TUNE_FAST_FILL: g_tune_fast = value; return 0;
         case PMRL_TUNE_RING_TMA: g_tune_rt = value; return 0;
         case PMRL_TUNE_STAGED: g_tune_staged = value; return 0;
+        case PMRL_TUNE_HOST_STREAM: pmrl_set_host_stream(value); return 0;
         default: return pmrl_fail(PMRL_E_ARG, "unknown tuning key");
     }
 }
@@ -524,6 +525,10 @@ static int prepare_step(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const Pmrl
     p.actions = io->actions; p.y_ext = io->y_ext; p.reward = io->reward; p.done = io->done; p.stats = io->stats;
     p.action_sink = io->action_sink; p.value_sink = io->value_sink; p.index_sink = io->index_sink; p.weight_sink = io->weight_sink;
     p.reward_host = io->reward_host; p.done_host = io->done_host;
+    if (io->actions_ready) {
+        if (io->actions_ready_shift < 0 || io->actions_ready_shift > 30) return pmrl_fail(PMRL_E_ARG, "bad actions_ready_shift");
+        p.act_ready = io->actions_ready; p.act_seq = io->actions_ready_seq; p.act_shift = io->actions_ready_shift;
+    }
     return 0;
 }
 

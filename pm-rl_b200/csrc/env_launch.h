@@ -13,3 +13,6 @@ int pmrl_launch_step_obs_fast(pmrl::StepParams& p, int npl, int vec, int group, 
 // State-only step for wide envs with the rows staged through shared memory by TMA bulk copies (env_step_staged.cu).
 // Returns -100 if the shape is not covered.
 int pmrl_launch_step_staged(const pmrl::StepParams& p, int npl, int vec, int shape, cudaStream_t s);
+
+// host_step.cu: 1 = stream page-locked actions in with the copy engine under the kernel (default), 0 = zero-copy reads.
+void pmrl_set_host_stream(int value);

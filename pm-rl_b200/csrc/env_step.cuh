@@ -234,6 +234,25 @@ __device__ __forceinline__ const float* env_y_row(const StepParams& p, int e, co
     return p.y_ext ? p.y_ext + (size_t)e * p.A : p.y_tm + (size_t)(s.t0e + s.k + p.W) * p.A;
 }
 
+// Streamed-in actions (PmrlStepIO.actions_ready): block until the chunk holding env e's row has landed in device memory.
+// One lane polls the flag with a system-scope acquire load (the writer is the copy engine: flag after data in stream order).
+__device__ __forceinline__ void env_wait_actions_lane(const StepParams& p, int e) {
+    const uint32_t* f = p.act_ready + (e >> p.act_shift);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v == p.act_seq) break;
+        if (spin > (1u << 22)) __trap();                             // ≈ seconds: a protocol bug traps instead of hanging the GPU
+        __nanosleep(128);
+    }
+}
+__device__ __forceinline__ void env_wait_actions(const StepParams& p, int e, int lane) {
+    if (p.act_ready) {
+        if (lane == 0) env_wait_actions_lane(p, e);
+        __syncwarp();
+    }
+}
+
 // Raw action, price relatives and (commission only) previous weights of env e into a lane's slots.
 // LOADWL = false: the caller supplies the previous weights itself (burst kernel: the w' it wrote one step earlier).
 // LOADY = false: the price relatives are fetched inside env_compute_store, after the mu iteration (wide envs with
@@ -242,6 +261,7 @@ template <int NPL, bool HASC, int VEC, bool TAIL = false, bool LOADWL = true, bo
 __device__ __forceinline__ void env_load_rows(const StepParams& p, int e, int lane, const EnvScalars& s,
                                               float (&va)[NPL], float (&vy)[NPL], float (&vwl)[HASC ? NPL : 1]) {
     if (env_needs_reset(p, s)) return;                           // nothing is read on the auto-reset call
+    env_wait_actions(p, e, lane);
     constexpr bool WL = HASC && LOADWL;
     const int A = p.A, W = p.W;
     const float* __restrict__ act = p.actions + (size_t)e * A;

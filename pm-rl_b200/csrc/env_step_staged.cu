@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(kStgWarps * 32, MINB) k_env_step_staged(const 
     auto issue = [&](int e, const EnvScalars& s, int st) {
         if (env_needs_reset(p, s)) return;                           // the auto-reset call reads nothing
         if (lane == 0) {
+            if (p.act_ready) { env_wait_actions_lane(p, e); asm volatile("fence.proxy.async;" ::: "memory"); }
             fence_proxy_async_smem();
             float* dst = my_rows + (size_t)st * R * A;
             uint64_t* bar = &s_bar[warp][st];
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(kStgWarps * 32, MINB) k_env_step_staged1(const
     if (e < p.E) {
         env_load_scalars(p, e, s0);
         if (!env_needs_reset(p, s0) && lane == 0) {
+            if (p.act_ready) { env_wait_actions_lane(p, e); asm volatile("fence.proxy.async;" ::: "memory"); }
             mbar_arrive_expect_tx(bar_a, (WLR ? 2u : 1u) * row_bytes);
             bulk_load_g2s(my_rows, p.actions + (size_t)e * A, row_bytes, bar_a, kPolicyEvictFirst);
             if (WLR) bulk_load_g2s(my_rows + 2 * A, wl_row(e, s0), row_bytes, bar_a, kPolicyEvictFirst);
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(kStgWarps * 32, MINB) k_env_step_staged1(const
         }
         __syncwarp();                                                // every lane holds its part of the action row
         if (next_live && lane == 0) {
+            if (p.act_ready) { env_wait_actions_lane(p, e + nw); asm volatile("fence.proxy.async;" ::: "memory"); }
             fence_proxy_async_smem();
             mbar_arrive_expect_tx(bar_a, (WLR ? 2u : 1u) * row_bytes);
             bulk_load_g2s(my_rows, p.actions + (size_t)(e + nw) * A, row_bytes, bar_a, kPolicyEvictFirst);

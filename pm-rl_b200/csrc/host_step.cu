@@ -18,18 +18,26 @@
 #include <string.h>
 #include "pmrl_b200.h"
 #include "host_util.h"
+#include "env_launch.h"
 
 namespace {
 
 constexpr int kMaxSlices = 32;
 constexpr int kMaxDevices = 64;
 
+constexpr int kMaxChunks = 64;
+
 struct HostPipe {
     bool ready = false;
-    std::mutex busy;                   // held for a whole sliced call: the streams and events below are per device
+    std::mutex busy;                   // held for a whole sliced / streamed call: the streams, events and flags below are per device
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t start = nullptr, in_ev[kMaxSlices], k_ev[kMaxSlices];
+    uint32_t* flags_dev = nullptr;     // [kMaxChunks] chunk-arrival flags of the streamed path (device memory)
+    uint32_t* seq_src = nullptr;       // [kMaxChunks] page-locked source of the flag writes (all = the call's sequence number)
+    uint32_t seq = 0;
 };
+
+int g_host_stream = 1;
 
 std::mutex g_mu;
 HostPipe g_pipes[kMaxDevices];
@@ -49,6 +57,9 @@ HostPipe* pipe_for_device() {
             if (cudaEventCreateWithFlags(&p.in_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
             if (cudaEventCreateWithFlags(&p.k_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         }
+        if (cudaMalloc((void**)&p.flags_dev, kMaxChunks * sizeof(uint32_t)) != cudaSuccess) return nullptr;
+        if (cudaMemset(p.flags_dev, 0, kMaxChunks * sizeof(uint32_t)) != cudaSuccess) return nullptr;
+        if (cudaHostAlloc((void**)&p.seq_src, kMaxChunks * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) return nullptr;
         p.ready = true;
     }
     return &p;
@@ -96,6 +107,8 @@ int slice_bounds(int E, int slices, int* bounds) {
 
 }  // namespace
 
+void pmrl_set_host_stream(int value) { g_host_stream = value; }
+
 extern "C" int pmrl_env_step_host(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
                                   const float* actions_host, float* actions_stage,
                                   float* reward, uint8_t* done, float* reward_host, uint8_t* done_host,
@@ -109,15 +122,74 @@ extern "C" int pmrl_env_step_host(const PmrlEnvCfg* cfg, const PmrlTables* tbl, 
     const size_t A = (size_t)cfg->A, WA = (size_t)cfg->W * A, obs_env = WA * (size_t)cfg->F;
 
     if (slices == 0) {
-        // zero-copy path: the kernel reads the mapped host actions itself and, when the result buffers are mapped too, writes
-        // reward / done straight into them (posted PCIe writes) — the call is then ONE launch and ONE synchronisation
-        if (const float* act_dev = mapped_alias(actions_host)) {
+        const float* act_dev = mapped_alias(actions_host);
+        float* r_dev = mapped_alias(reward_host);
+        uint8_t* d_dev = mapped_alias(done_host);
+        const bool mirrored = r_dev && d_dev;           // the kernel writes reward / done straight into mapped host memory (posted PCIe writes)
+        // Where streaming pays (measured, 1 x B200): with the obs materialised the kernel is long enough to hide the copy engine's
+        // fixed cost per copy (config 4 shard 2.773 → 2.738 ms, config 3 1.438 → 1.410 ms end to end); a state-only step is PCIe-bound
+        // either way, and the dozen copies cost more than they save until the batch is large (131,072 x 100: 1.21 ms zero-copy vs
+        // 1.38 ms streamed; 262,144 x 500: 10.66 vs 9.94 ms).  Small batches keep the zero-copy reads: one PCIe round trip costs
+        // less than waiting for a DMA chunk.
+        const size_t act_bytes = (size_t)cfg->E * A * sizeof(float);
+        const size_t stream_from = obs_mode == PMRL_OBS_FULL ? ((size_t)2 << 20) : ((size_t)128 << 20);
+        if (act_dev && (g_host_stream == 2 || (g_host_stream == 1 && act_bytes >= stream_from))) {
+            // streamed path (default): ONE kernel over the whole batch, launched at once, while the copy engine brings the
+            // action rows into device memory chunk by chunk behind it; every chunk is followed on the copy stream by a 4-byte
+            // flag write, and a warp waits for the flag of its env's chunk before it reads the row (PmrlStepIO.actions_ready).
+            // The groups are taken in ascending env order, the copy runs at PCIe speed (52 MB in ≈1 ms at config 4) against
+            // a 2.7 ms kernel, so only the first chunk is ever waited for.  Unlike zero-copy reads the step phase never pays a
+            // PCIe round trip (L2 prefetch does not apply to host memory), and unlike the sliced pipeline there are no kernel
+            // boundaries.  The flags carry a per-call sequence number, so they are never reset.
+            HostPipe* hp = pipe_for_device();
+            if (!hp) return pmrl_fail(PMRL_E_ARG, "env_step_host: could not create the copy streams");
+            std::lock_guard<std::mutex> busy(hp->busy);
+            int shift = 0;
+            while (((cfg->E + (1 << shift) - 1) >> shift) > 32 || ((size_t)(1 << shift) * A * sizeof(float) < (256u << 10) && (1 << shift) < cfg->E)) ++shift;
+            const int n = (cfg->E + (1 << shift) - 1) >> shift;
+            if (n <= kMaxChunks) {
+                if (++hp->seq == 0) hp->seq = 1;
+                for (int c = 0; c < n; ++c) hp->seq_src[c] = hp->seq;
+                PMRL_CUDA(cudaEventRecord(hp->start, s), "env_step_host: event record");
+                PMRL_CUDA(cudaStreamWaitEvent(hp->copy_in, hp->start, 0), "env_step_host: stream wait");   // earlier work on s may still read the stage
+                PmrlStepIO io;
+                memset(&io, 0, sizeof(io));
+                io.actions = actions_stage; io.reward = reward; io.done = done; io.obs = obs; io.obs_mode = obs_mode; io.stats = stats;
+                io.actions_ready = hp->flags_dev; io.actions_ready_seq = hp->seq; io.actions_ready_shift = shift;
+                if (mirrored) { io.reward_host = r_dev; io.done_host = d_dev; }
+                int rc = pmrl_env_step_io(cfg, tbl, st, &io, stream);           // the kernel first: it waits on the flags, not the host on it
+                if (rc != 0) return rc;
+                // copies cover 1, 1, 2, 4, 8, … chunks each (a small first copy so the kernel starts early, few large ones after
+                // it: every copy and every 4-byte-per-chunk flag write costs the copy engine a fixed few microseconds)
+                for (int c = 0, c1 = 0; c < n; c = c1) {
+                    c1 = c < 2 ? c + 1 : 2 * c;                      // [0,1) [1,2) [2,4) [4,8) …
+                    if (c1 > n) c1 = n;
+                    const size_t lo = (size_t)c << shift;
+                    const size_t hi = ((size_t)c1 << shift) < (size_t)cfg->E ? ((size_t)c1 << shift) : (size_t)cfg->E;
+                    cudaError_t e1 = cudaMemcpyAsync(actions_stage + lo * A, actions_host + lo * A, (hi - lo) * A * sizeof(float), cudaMemcpyHostToDevice, hp->copy_in);
+                    cudaError_t e2 = cudaMemcpyAsync(hp->flags_dev + c, hp->seq_src + c, (size_t)(c1 - c) * sizeof(uint32_t), cudaMemcpyHostToDevice, hp->copy_in);
+                    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+                        // the kernel is waiting for these chunks: release it with the flags alone (the rows are garbage, the call fails)
+                        cudaMemcpyAsync(hp->flags_dev + c, hp->seq_src + c, (size_t)(n - c) * sizeof(uint32_t), cudaMemcpyHostToDevice, hp->copy_in);
+                        cudaStreamSynchronize(hp->copy_in); cudaStreamSynchronize(s);
+                        pmrl_fail((int)(e1 != cudaSuccess ? e1 : e2), "env_step_host: H2D action chunk");
+                        return (int)(e1 != cudaSuccess ? e1 : e2);
+                    }
+                }
+                if (!mirrored) {
+                    PMRL_CUDA(cudaMemcpyAsync(reward_host, reward, (size_t)cfg->E * sizeof(float), cudaMemcpyDeviceToHost, s), "env_step_host: D2H reward");
+                    PMRL_CUDA(cudaMemcpyAsync(done_host, done, (size_t)cfg->E, cudaMemcpyDeviceToHost, s), "env_step_host: D2H done");
+                }
+                PMRL_CUDA(cudaStreamSynchronize(s), "env_step_host: synchronize");
+                PMRL_CUDA(cudaStreamSynchronize(hp->copy_in), "env_step_host: synchronize");   // (chunks of envs that only auto-reset are not waited for by the kernel)
+                return 0;
+            }
+        }
+        // zero-copy path: the kernel reads the mapped host actions itself over PCIe — ONE launch and ONE synchronisation
+        if (act_dev) {
             PmrlStepIO io;
             memset(&io, 0, sizeof(io));
             io.actions = act_dev; io.reward = reward; io.done = done; io.obs = obs; io.obs_mode = obs_mode; io.stats = stats;
-            float* r_dev = mapped_alias(reward_host);
-            uint8_t* d_dev = mapped_alias(done_host);
-            const bool mirrored = r_dev && d_dev;
             if (mirrored) { io.reward_host = r_dev; io.done_host = d_dev; }
             int rc = pmrl_env_step_io(cfg, tbl, st, &io, stream);
             if (rc != 0) return rc;

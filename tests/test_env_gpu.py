@@ -96,7 +96,7 @@ def tuning():
     yield _lib
     for k in (_lib.TUNE_GROUP_ENVS, _lib.TUNE_CTAS_PER_SM):
         _lib.set_tuning(k, 0)
-    for k in (_lib.TUNE_FUSED, _lib.TUNE_RING_TMA, _lib.TUNE_FAST_FILL, _lib.TUNE_STAGED):
+    for k in (_lib.TUNE_FUSED, _lib.TUNE_RING_TMA, _lib.TUNE_FAST_FILL, _lib.TUNE_STAGED, _lib.TUNE_HOST_STREAM):
         _lib.set_tuning(k, 1)
 
 
@@ -568,6 +568,33 @@ def test_step_host_chunked_matches_step(E, chunks, pinned):
     compare_state(gpu, ora, "end")
     compare_obs(obs, ora, "end")
     assert gpu.stats()["n_envs"] == E * (L + 4) - E      # one auto-reset call per env is not a step
+
+
+@pytest.mark.parametrize("E,A,W,commission,obs,stream", [(700, 40, 8, 0.0, True, 2), (4096, 100, 12, 0.0, True, 2), (3000, 500, 6, 0.0025, False, 2),
+                                                         (3000, 500, 6, 0.0025, True, 2), (9000, 100, 10, 0.0, True, 1), (333, 7, 5, 0.0, True, 2),
+                                                         (4096, 100, 12, 0.0, True, 0), (5000, 52, 50, 0.001, False, 2)])
+def test_step_host_streamed_actions(E, A, W, commission, obs, stream, tuning):
+    """pmrl_env_step_host with page-locked actions: the kernel is launched at once and waits per chunk for the action rows
+    the copy engine streams in behind it (PmrlStepIO.actions_ready; stream = 2 forces the path at any size, 1 = by size,
+    0 = zero-copy reads) — same transition as the oracle, auto-resets (envs that read no action) included, through the
+    fused, the two-kernel, the register-load and the staged wide-env kernels."""
+    L = W + 5
+    tuning.set_tuning(tuning.TUNE_HOST_STREAM, stream)
+    tuning.set_tuning(tuning.TUNE_STAGED, 2)
+    gpu, ora = make_pair(E, A, W, 5, episode_len=L, commission=commission)
+    gpu.reset(obs=obs)
+    g = torch.Generator().manual_seed(E + A)
+    h_r = torch.empty(E, dtype=torch.float32).pin_memory(); h_d = torch.empty(E, dtype=torch.uint8).pin_memory()
+    acts = [torch.randn(E, A, generator=g).pin_memory() for _ in range(3)]
+    for s in range(L + 3):
+        act = acts[s % 3]
+        o, r, d = gpu.step_host(act, h_r, h_d, obs=obs)
+        r_o, d_o = ora.step(act.numpy())
+        util.assert_rewards_close(r.numpy(), r_o, f"step {s}")
+        np.testing.assert_array_equal(d.numpy(), d_o)
+    compare_state(gpu, ora, "end")
+    if obs:
+        compare_obs(o, ora, "end")
 
 
 @pytest.mark.parametrize("seed", range(24))
