@@ -180,6 +180,8 @@ const char* pmrl_last_error(void);
                                      of >= 2 MB of actions with the obs materialised (>= 128 MB state-only), others take the
                                      zero-copy path; 2: streamed at any size;
                                      0: zero-copy, the kernel reads the host buffer over PCIe itself */
+#define PMRL_TUNE_HOST_MIRROR 14  /* pmrl_env_step_host with page-locked result buffers: 1 the kernel writes reward / done straight into
+                                     the mapped host buffers; 0 two device→host copies after the kernel */
 int pmrl_set_tuning(int32_t key, int32_t value);
 
 /* Kernels this library has launched in this process so far (every entry point counts its own launches; bench.py reports

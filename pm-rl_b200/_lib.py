@@ -138,7 +138,7 @@ def current_stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-TUNE_GROUP_ENVS, TUNE_CTAS_PER_SM, TUNE_FUSED, TUNE_FAST_FILL, TUNE_RING_TMA, TUNE_STAGED, TUNE_HOST_STREAM = 2, 3, 4, 5, 11, 12, 13
+TUNE_GROUP_ENVS, TUNE_CTAS_PER_SM, TUNE_FUSED, TUNE_FAST_FILL, TUNE_RING_TMA, TUNE_STAGED, TUNE_HOST_STREAM, TUNE_HOST_MIRROR = 2, 3, 4, 5, 11, 12, 13, 14
 
 
 def set_tuning(key: int, value: int) -> None:

@@ -417,6 +417,7 @@ extern "C" int pmrl_set_tuning(int32_t key, int32_t value) {
         case PMRL_TUNE_RING_TMA: g_tune_rt = value; return 0;
         case PMRL_TUNE_STAGED: g_tune_staged = value; return 0;
         case PMRL_TUNE_HOST_STREAM: pmrl_set_host_stream(value); return 0;
+        case PMRL_TUNE_HOST_MIRROR: pmrl_set_host_mirror(value); return 0;
         default: return pmrl_fail(PMRL_E_ARG, "unknown tuning key");
     }
 }

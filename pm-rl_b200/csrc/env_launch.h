@@ -16,3 +16,4 @@ int pmrl_launch_step_staged(const pmrl::StepParams& p, int npl, int vec, int sha
 
 // host_step.cu: 1 = stream page-locked actions in with the copy engine under the kernel (default), 0 = zero-copy reads.
 void pmrl_set_host_stream(int value);
+void pmrl_set_host_mirror(int value);

@@ -37,7 +37,7 @@ struct HostPipe {
     uint32_t seq = 0;
 };
 
-int g_host_stream = 1;
+int g_host_stream = 1, g_host_mirror = 1;
 
 std::mutex g_mu;
 HostPipe g_pipes[kMaxDevices];
@@ -108,6 +108,7 @@ int slice_bounds(int E, int slices, int* bounds) {
 }  // namespace
 
 void pmrl_set_host_stream(int value) { g_host_stream = value; }
+void pmrl_set_host_mirror(int value) { g_host_mirror = value; }
 
 extern "C" int pmrl_env_step_host(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlEnvState* st,
                                   const float* actions_host, float* actions_stage,
@@ -125,12 +126,13 @@ extern "C" int pmrl_env_step_host(const PmrlEnvCfg* cfg, const PmrlTables* tbl, 
         const float* act_dev = mapped_alias(actions_host);
         float* r_dev = mapped_alias(reward_host);
         uint8_t* d_dev = mapped_alias(done_host);
-        const bool mirrored = r_dev && d_dev;           // the kernel writes reward / done straight into mapped host memory (posted PCIe writes)
-        // Where streaming pays (measured, 1 x B200): with the obs materialised the kernel is long enough to hide the copy engine's
-        // fixed cost per copy (config 4 shard 2.773 → 2.738 ms, config 3 1.438 → 1.410 ms end to end); a state-only step is PCIe-bound
-        // either way, and the dozen copies cost more than they save until the batch is large (131,072 x 100: 1.21 ms zero-copy vs
-        // 1.38 ms streamed; 262,144 x 500: 10.66 vs 9.94 ms).  Small batches keep the zero-copy reads: one PCIe round trip costs
-        // less than waiting for a DMA chunk.
+        const bool mirrored = g_host_mirror && r_dev && d_dev;   // the kernel writes reward / done straight into mapped host memory (posted PCIe writes)
+        // Where streaming pays (measured, 1 x B200, tools/e2e_ab.py): with the obs materialised the kernel is long enough to hide
+        // the copy engine's fixed cost per copy — on one box config 4 shard 2.773 → 2.738 ms, config 3 1.438 → 1.410 ms end to end,
+        // on another the two modes were equal within the run-to-run spread; a state-only step is PCIe-bound either way, and the
+        // dozen copies cost more than they save until the batch is large (131,072 x 100: 1.21 ms zero-copy vs 1.38 ms streamed;
+        // 262,144 x 500: 10.66 vs 9.94 ms).  Small batches keep the zero-copy reads: one PCIe round trip costs less than
+        // waiting for a DMA chunk (4,096 x 50: 94 us vs 105 us).
         const size_t act_bytes = (size_t)cfg->E * A * sizeof(float);
         const size_t stream_from = obs_mode == PMRL_OBS_FULL ? ((size_t)2 << 20) : ((size_t)128 << 20);
         if (act_dev && (g_host_stream == 2 || (g_host_stream == 1 && act_bytes >= stream_from))) {
