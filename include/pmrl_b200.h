@@ -163,7 +163,8 @@ const char* pmrl_last_error(void);
 /* Launch-shape tuning hook (process-wide; for benchmarking the kernel variants, not part of the reference surface).
  * value <= 0 restores the built-in heuristic. */
 #define PMRL_TUNE_GROUP_ENVS  2   /* envs a CTA advances together (1..16) */
-#define PMRL_TUNE_CTAS_PER_SM 3   /* persistent CTAs per SM */
+#define PMRL_TUNE_CTAS_PER_SM 3   /* persistent CTAs per SM of the fused step+obs kernel; for the staged wide-env step: 3 = three 8-warp CTAs
+                                     with single-stage rows (default: two CTAs, double-buffered rows) */
 #define PMRL_TUNE_FUSED       4   /* 1 (default): fused step+obs kernel where one covers the shape, else k_env_step followed by the
                                      obs tile kernel; 0: always the two kernels */
 #define PMRL_TUNE_FAST_FILL   5   /* 1 (default): specialised obs kernels (fused RT / register-staged, division-free tile fill);

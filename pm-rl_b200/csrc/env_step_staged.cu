@@ -5,10 +5,10 @@
 // Why: a 500-asset env is 16 slots per lane; with action + previous weights + price relatives in registers there is no room
 // for a second env's rows, so k_env_step (env_kernels.cu) could only pull the next env's rows into L2 and then paid an L2
 // round trip per row at the head of every env (ncu, config 5: 3.0 warps per scheduler stalled on the long scoreboard, issue
-// slots 59 % busy, 8 spilled registers at the 80-register / 3-CTA build).  Here the DRAM latency is taken by the copy
-// engine: a warp finds its rows in shared memory (ld.shared.v4, conflict-free: lane-consecutive 16-byte groups), the price
-// relatives are read after the mu iteration straight from the staged row (no registers held for them), and 128 registers
-// at two CTAs per SM leave nothing spilled.  The arithmetic is env_compute_rows of env_step.cuh — the same operations in
+// slots 59 % busy, 8 spilled registers at the 80-register / 3-CTA build: 0.390 ms on config 5).  Here the DRAM latency is
+// taken by the TMA unit: a warp finds its rows in shared memory (ld.shared.v4, conflict-free: lane-consecutive 16-byte groups), the price
+// relatives are read after the mu iteration straight from the staged row (no registers held for them), and 107 registers
+// at two CTAs per SM leave nothing spilled: 0.335 ms (0.72 of the HBM roofline, instruction-issue-bound).  The arithmetic is env_compute_rows of env_step.cuh — the same operations in
 // the same order as every other step kernel (cross-kernel bit-identity is asserted in tests/test_env_gpu.py).
 //
 // Shared memory per warp: 2 stages x R rows x A floats (R = 3 with commission, else 2): 12,000 B at A = 500 → 96 KB per
