@@ -218,15 +218,18 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
         Feat fr;
         if (nfull > 0) load_feat(fr, 0, std::false_type{}); else load_feat(fr, 0, std::true_type{});
         for (int ti = 0; ti < ntiles; ++ti) {
+            // ONE CTA barrier per tile.  The buffer filled now was last read by the bulk store issued two tiles ago; thread 0
+            // waited for that store to finish reading shared memory BEFORE it arrived at the previous tile's barrier, so
+            // every thread that is past that barrier may overwrite it.  (Round 1 had a second barrier at the top of the tile
+            // for exactly this hand-over; barrier stalls were the largest stall reason, 2.0 per issue at F = 5, 2.8 at F = 9.)
             float* const tile = buf ? tile1 : tile0;
-            if (tid == 0) bulk_wait_read<1>();                        // the store that last used this buffer has drained
-            __syncthreads();
             const int r0 = ti * TR;
             if (ti < nfull) spill_tile(fr, tile, r0, std::false_type{}); else spill_tile(fr, tile, r0, std::true_type{});
             if (ti + 1 < ntiles) {
                 if (ti + 1 < nfull) load_feat(fr, r0 + TR, std::false_type{}); else load_feat(fr, r0 + TR, std::true_type{});
             }
             fence_proxy_async_smem();
+            if (tid == 0) bulk_wait_read<0>();                        // the previous tile's store (other buffer) has drained: see above
             __syncthreads();
             const int nr = min(TR, R - r0);
             float* const gdst = obs_grp + (size_t)r0 * row_floats;
@@ -234,8 +237,8 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
             if (((((uintptr_t)gdst) | ((size_t)n * 4)) & 15) == 0) {
                 if (tid == 0) { bulk_store_s2g(gdst, tile, (uint32_t)n * 4u, kPolicyEvictFirst); bulk_commit(); }
             } else {
-                for (int q = tid; q < n; q += kRtThreads) gdst[q] = tile[q];
-            }
+                for (int q = tid; q < n; q += kRtThreads) gdst[q] = tile[q];   // (done before this thread reaches the next barrier,
+            }                                                                  //  and the tile is refilled only after that one)
             // envs below (r0+TR)/A are complete (every thread passed the barrier after its last read of their ring):
             // their buffers can take the rings of the envs NB positions further on
             if (tid == 0) issue_rings(min(ne, (r0 + TR) / A + NB));
