@@ -367,9 +367,8 @@ def measure_e2e(ctx, env, pool, E, A, obs, steps, chunks=0):
     ems = ctx.max_over_ranks(e0.elapsed_time(e1))
     return {"value": ctx.world * E * A * steps / (ems * 1e-3), "unit": "asset-steps/s",
             "h2d_bytes_per_step": E * A * 4, "d2h_bytes_per_step": E * 5, "chunks": chunks,
-            "transfer": ("streamed: one kernel launched at once, the copy engine brings the pinned action rows in chunk by chunk behind it "
-                         "(the kernel waits per chunk); reward/done written by the kernel into mapped pinned memory; batches under 2 MB of "
-                         "actions: zero-copy PCIe reads" if chunks == 0 else "sliced H2D/D2H copies overlapped with per-slice kernels"),
+            "transfer": ("zero-copy: ONE kernel reads the pinned host actions over PCIe and writes reward/done into mapped pinned memory"
+                         if chunks == 0 else "sliced H2D/D2H copies overlapped with per-slice kernels"),
             "api": "BatchedTradingEnv.step_host -> C-ABI pmrl_env_step_host",
             "ms_per_step": ems / steps}
 

@@ -176,11 +176,11 @@ const char* pmrl_last_error(void);
                                      price-relative rows staged one env ahead through shared memory by TMA bulk copies
                                      (env_step_staged.cu) when a warp has more than one env; 2: also for small batches; 0: register loads +
                                      L2 prefetch (k_env_step) */
-#define PMRL_TUNE_HOST_STREAM 13  /* pmrl_env_step_host with page-locked actions: 1 (default) the copy engine streams the action rows
-                                     into device memory in chunks UNDER the kernel, which waits per chunk (PmrlStepIO.actions_ready) — for batches
-                                     of >= 2 MB of actions with the obs materialised (>= 128 MB state-only), others take the
-                                     zero-copy path; 2: streamed at any size;
-                                     0: zero-copy, the kernel reads the host buffer over PCIe itself */
+#define PMRL_TUNE_HOST_STREAM 13  /* pmrl_env_step_host with page-locked actions: 0 (default) zero-copy, the kernel reads the host buffer
+                                     over PCIe itself; 1: the copy engine streams the action rows into device memory in chunks under
+                                     the kernel, which waits per chunk (PmrlStepIO.actions_ready), for batches of >= 2 MB of actions
+                                     with the obs materialised (>= 128 MB state-only); 2: streamed at any size.  Measured equal
+                                     within the run-to-run spread, hence not the default */
 #define PMRL_TUNE_HOST_MIRROR 14  /* pmrl_env_step_host with page-locked result buffers: 1 the kernel writes reward / done straight into
                                      the mapped host buffers; 0 two device→host copies after the kernel */
 int pmrl_set_tuning(int32_t key, int32_t value);

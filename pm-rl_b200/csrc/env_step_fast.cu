@@ -159,9 +159,9 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs_fast(const
             const int nfull = R >> 5;                      // tiles with all 32 asset-rows
             constexpr int RA = 1;
             auto emit = [&](FeatRegs& fr, RingRegs& rr, int ti) {   // registers → shared tile → TMA store; refill the registers
+                // one CTA barrier per tile: thread 0 waits for the previous tile's store (other buffer) to finish reading shared
+                // memory before it arrives at THIS tile's barrier, so past that barrier the other buffer is free (env_step_rt.cu)
                 float* const tile = buf ? tile1 : tile0;
-                if (tid == 0) bulk_wait_read<1>();        // the store that last used this buffer has drained
-                __syncthreads();
                 const int r0 = ti * 32;
                 if (ti < nfull) spill_tile(fr, rr, tile, r0, std::false_type{}); else spill_tile(fr, rr, tile, r0, std::true_type{});
                 if (ti + 1 < ntiles) {                    // table loads of the next tile first (L2 hits) ...
@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_env_step_obs_fast(const
                 if (RING2) __syncwarp();                  // keeps the ring loads behind the table loads in issue order
                 if (ti + RA < ntiles) load_ring(rr, r0 + 32 * RA);   // ... then the DRAM-latency ring loads
                 fence_proxy_async_smem();
+                if (tid == 0) bulk_wait_read<0>();
                 __syncthreads();
                 const int nr = min(32, R - r0);
                 float* const gdst = obs_grp + (size_t)r0 * row_floats;

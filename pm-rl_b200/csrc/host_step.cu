@@ -37,7 +37,7 @@ struct HostPipe {
     uint32_t seq = 0;
 };
 
-int g_host_stream = 1, g_host_mirror = 1;
+int g_host_stream = 0, g_host_mirror = 1;
 
 std::mutex g_mu;
 HostPipe g_pipes[kMaxDevices];
@@ -127,18 +127,17 @@ extern "C" int pmrl_env_step_host(const PmrlEnvCfg* cfg, const PmrlTables* tbl, 
         float* r_dev = mapped_alias(reward_host);
         uint8_t* d_dev = mapped_alias(done_host);
         const bool mirrored = g_host_mirror && r_dev && d_dev;   // the kernel writes reward / done straight into mapped host memory (posted PCIe writes)
-        // Where streaming pays (measured, 1 x B200, tools/e2e_ab.py): with the obs materialised the kernel is long enough to hide
-        // the copy engine's fixed cost per copy — on one box config 4 shard 2.773 → 2.738 ms, config 3 1.438 → 1.410 ms end to end,
-        // on another the two modes were equal within the run-to-run spread; a state-only step is PCIe-bound either way, and the
-        // dozen copies cost more than they save until the batch is large (131,072 x 100: 1.21 ms zero-copy vs 1.38 ms streamed;
-        // 262,144 x 500: 10.66 vs 9.94 ms).  Small batches keep the zero-copy reads: one PCIe round trip costs less than
-        // waiting for a DMA chunk (4,096 x 50: 94 us vs 105 us).
+        // Streaming vs zero-copy reads, measured on three boxes (tools/e2e_ab.py, alternating repetitions on one box): with the
+        // obs materialised one box gave config 4 shard 2.773 → 2.738 ms and config 3 1.438 → 1.410 ms, two others gave equal
+        // times at config 4 (2.81–2.89 ms in both modes) and streaming 2.5 % SLOWER at config 3; state-only steps are PCIe-bound
+        // either way (131,072 x 100: 1.21 ms zero-copy vs 1.38 ms streamed; 262,144 x 500: 10.66 vs 9.94 ms); small batches lose
+        // (4,096 x 50: 94 us vs 105 us).  No robust gain → zero-copy is the default and streaming stays an option.
         const size_t act_bytes = (size_t)cfg->E * A * sizeof(float);
         const size_t stream_from = obs_mode == PMRL_OBS_FULL ? ((size_t)2 << 20) : ((size_t)128 << 20);
         if (act_dev && (g_host_stream == 2 || (g_host_stream == 1 && act_bytes >= stream_from))) {
-            // streamed path (default): ONE kernel over the whole batch, launched at once, while the copy engine brings the
-            // action rows into device memory chunk by chunk behind it; every chunk is followed on the copy stream by a 4-byte
-            // flag write, and a warp waits for the flag of its env's chunk before it reads the row (PmrlStepIO.actions_ready).
+            // streamed path (opt-in, PMRL_TUNE_HOST_STREAM): ONE kernel over the whole batch while the copy engine brings the action rows into
+            // device memory chunk by chunk; every group of chunks is followed on the copy stream by its flag words, and
+            // a warp waits for the flag of its env's chunk before it reads the row (PmrlStepIO.actions_ready).
             // The groups are taken in ascending env order, the copy runs at PCIe speed (52 MB in ≈1 ms at config 4) against
             // a 2.7 ms kernel, so only the first chunk is ever waited for.  Unlike zero-copy reads the step phase never pays a
             // PCIe round trip (L2 prefetch does not apply to host memory), and unlike the sliced pipeline there are no kernel
@@ -154,30 +153,30 @@ extern "C" int pmrl_env_step_host(const PmrlEnvCfg* cfg, const PmrlTables* tbl, 
                 for (int c = 0; c < n; ++c) hp->seq_src[c] = hp->seq;
                 PMRL_CUDA(cudaEventRecord(hp->start, s), "env_step_host: event record");
                 PMRL_CUDA(cudaStreamWaitEvent(hp->copy_in, hp->start, 0), "env_step_host: stream wait");   // earlier work on s may still read the stage
-                PmrlStepIO io;
-                memset(&io, 0, sizeof(io));
-                io.actions = actions_stage; io.reward = reward; io.done = done; io.obs = obs; io.obs_mode = obs_mode; io.stats = stats;
-                io.actions_ready = hp->flags_dev; io.actions_ready_seq = hp->seq; io.actions_ready_shift = shift;
-                if (mirrored) { io.reward_host = r_dev; io.done_host = d_dev; }
-                int rc = pmrl_env_step_io(cfg, tbl, st, &io, stream);           // the kernel first: it waits on the flags, not the host on it
-                if (rc != 0) return rc;
-                // copies cover 1, 1, 2, 4, 8, … chunks each (a small first copy so the kernel starts early, few large ones after
-                // it: every copy and every 4-byte-per-chunk flag write costs the copy engine a fixed few microseconds)
+                // The copies are enqueued BEFORE the kernel: a launch that blocks the host (a profiler or debugger serialising
+                // kernels, CUDA_LAUNCH_BLOCKING=1) must find every chunk it will wait for already on its way.  They cover
+                // 2, 4, 8, 18 chunks (a small first copy so the kernel finds its first rows on arrival, few large ones after it:
+                // every copy and every flag write costs the copy engine and the host a fixed few microseconds).
                 for (int c = 0, c1 = 0; c < n; c = c1) {
-                    c1 = c < 2 ? c + 1 : 2 * c;                      // [0,1) [1,2) [2,4) [4,8) …
+                    c1 = c == 0 ? 2 : c == 2 ? 6 : c == 6 ? 14 : n;
                     if (c1 > n) c1 = n;
                     const size_t lo = (size_t)c << shift;
                     const size_t hi = ((size_t)c1 << shift) < (size_t)cfg->E ? ((size_t)c1 << shift) : (size_t)cfg->E;
                     cudaError_t e1 = cudaMemcpyAsync(actions_stage + lo * A, actions_host + lo * A, (hi - lo) * A * sizeof(float), cudaMemcpyHostToDevice, hp->copy_in);
                     cudaError_t e2 = cudaMemcpyAsync(hp->flags_dev + c, hp->seq_src + c, (size_t)(c1 - c) * sizeof(uint32_t), cudaMemcpyHostToDevice, hp->copy_in);
                     if (e1 != cudaSuccess || e2 != cudaSuccess) {
-                        // the kernel is waiting for these chunks: release it with the flags alone (the rows are garbage, the call fails)
-                        cudaMemcpyAsync(hp->flags_dev + c, hp->seq_src + c, (size_t)(n - c) * sizeof(uint32_t), cudaMemcpyHostToDevice, hp->copy_in);
-                        cudaStreamSynchronize(hp->copy_in); cudaStreamSynchronize(s);
+                        cudaStreamSynchronize(hp->copy_in);
                         pmrl_fail((int)(e1 != cudaSuccess ? e1 : e2), "env_step_host: H2D action chunk");
                         return (int)(e1 != cudaSuccess ? e1 : e2);
                     }
                 }
+                PmrlStepIO io;
+                memset(&io, 0, sizeof(io));
+                io.actions = actions_stage; io.reward = reward; io.done = done; io.obs = obs; io.obs_mode = obs_mode; io.stats = stats;
+                io.actions_ready = hp->flags_dev; io.actions_ready_seq = hp->seq; io.actions_ready_shift = shift;
+                if (mirrored) { io.reward_host = r_dev; io.done_host = d_dev; }
+                int rc = pmrl_env_step_io(cfg, tbl, st, &io, stream);
+                if (rc != 0) { cudaStreamSynchronize(hp->copy_in); return rc; }
                 if (!mirrored) {
                     PMRL_CUDA(cudaMemcpyAsync(reward_host, reward, (size_t)cfg->E * sizeof(float), cudaMemcpyDeviceToHost, s), "env_step_host: D2H reward");
                     PMRL_CUDA(cudaMemcpyAsync(done_host, done, (size_t)cfg->E, cudaMemcpyDeviceToHost, s), "env_step_host: D2H done");

@@ -98,8 +98,9 @@ def tuning():
     yield _lib
     for k in (_lib.TUNE_GROUP_ENVS, _lib.TUNE_CTAS_PER_SM):
         _lib.set_tuning(k, 0)
-    for k in (_lib.TUNE_FUSED, _lib.TUNE_RING_TMA, _lib.TUNE_FAST_FILL, _lib.TUNE_STAGED, _lib.TUNE_HOST_STREAM):
+    for k in (_lib.TUNE_FUSED, _lib.TUNE_RING_TMA, _lib.TUNE_FAST_FILL, _lib.TUNE_STAGED):
         _lib.set_tuning(k, 1)
+    _lib.set_tuning(_lib.TUNE_HOST_STREAM, 0)
 
 
 # (fused, group_envs, ring_tma, fast_fill): the fused step+obs kernel in several launch shapes — ring-through-TMA kernel (default, with

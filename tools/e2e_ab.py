@@ -37,7 +37,7 @@ def main():
                     for i in range(20):
                         t0 = time.perf_counter(); env.step_host(acts[i % 2], h_r, h_d, obs=obs); ts.append((time.perf_counter() - t0) * 1e3)
                     res.setdefault(("stream" if mode else "zerocopy") + ("+mirror" if mirror else "+d2h"), []).append(round(statistics.median(ts), 4))
-        _lib.set_tuning(_lib.TUNE_HOST_STREAM, 1); _lib.set_tuning(_lib.TUNE_HOST_MIRROR, 1)
+        _lib.set_tuning(_lib.TUNE_HOST_STREAM, 0); _lib.set_tuning(_lib.TUNE_HOST_MIRROR, 1)
         print(json.dumps(res), flush=True)
         del env
 

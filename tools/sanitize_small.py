@@ -9,7 +9,7 @@ from pmrl_b200 import _lib, synth, features
 from pmrl_b200.buffers import DeviceRolloutBuffer
 from pmrl_b200.env import BatchedTradingEnv
 
-DEFAULTS = {_lib.TUNE_FUSED: 1, _lib.TUNE_FAST_FILL: 1, _lib.TUNE_RING_TMA: 1, _lib.TUNE_STAGED: 1, _lib.TUNE_HOST_STREAM: 1,
+DEFAULTS = {_lib.TUNE_FUSED: 1, _lib.TUNE_FAST_FILL: 1, _lib.TUNE_RING_TMA: 1, _lib.TUNE_STAGED: 1, _lib.TUNE_HOST_STREAM: 0,
             _lib.TUNE_GROUP_ENVS: 0, _lib.TUNE_CTAS_PER_SM: 0}
 
 
