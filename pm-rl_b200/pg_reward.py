@@ -10,6 +10,9 @@ import torch
 from . import _lib
 
 _MODES = {"returns": 1, "log_returns": 2}
+# "sharpe_ratio" (pg.py:79-80: mean(ret) / std(ret) * REWARD_SCALE over the batch) is a batch-level statistic: the kernel
+# supplies the per-row gross return and its Jacobian wrt the raw action (RETURNS mode), the two batch reductions and the
+# chain rule  dr/dret_b = [1/(B s) - m (ret_b - m) / ((B - 1) s^3)] * scale  are a handful of device ops on [B] vectors.
 
 
 def reference_normalise_condition(a) -> bool:
@@ -21,6 +24,15 @@ def pg_reward(a, pv, pa, p, mode: str = "log_returns", normalise: bool = True, c
               scale: float = 1.0, gscale: float = 1.0, mu_max_iter: int = 16, want_grad: bool = True):
     """a [B, A(,1)] raw actions, pv [B(,1,1)] previous values, pa [B, A(,1)] previous weights, p [B, A(,1)] price relatives.
     Returns (rew [B], grad_a [B, A] = gscale * d mean(rew) / d a  or None)."""
+    if mode == "sharpe_ratio":
+        B = a.shape[0]
+        ret, jac = pg_reward(a, pv, pa, p, "returns", normalise, commission, 1.0, float(B), mu_max_iter, want_grad)   # jac = d ret_b / d a_b
+        m, sd = ret.mean(), ret.std()                            # torch.std: unbiased (ddof = 1), like the reference
+        rew = (m / sd * scale).expand(B)                         # the reference returns ONE scalar; mean over [B] gives it back
+        if not want_grad:
+            return rew, None
+        coef = (1.0 / (B * sd) - m * (ret - m) / ((B - 1) * sd ** 3)) * (scale * gscale)
+        return rew, jac * coef[:, None]
     lib = _lib.load()
     B = a.shape[0]
     A = a.numel() // max(B, 1)

@@ -56,7 +56,7 @@ def pg_reward():
     importlib.reload(net); importlib.reload(pg)
     out = {}
     rs = np.random.RandomState(4)
-    for mode in ("log_returns", "returns"):
+    for mode in ("log_returns", "returns", "sharpe_ratio"):
         pg.REWARD = mode
         agent = pg.PG.__new__(pg.PG)                     # _reward needs no network
         B = 16

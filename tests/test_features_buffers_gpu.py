@@ -213,15 +213,22 @@ def test_replay_buffer_matches_reference_golden(tag, sampler):
 
 
 # ---------------------------------------------------------------- PG reward (fwd + grad) and eval metrics
-@pytest.mark.parametrize("mode", ["log_returns", "returns"])
+@pytest.mark.parametrize("mode", ["log_returns", "returns", "sharpe_ratio"])
 def test_pg_reward_matches_reference_autograd(mode):
     from pmrl_b200.pg_reward import pg_reward
     g = golden("pg_reward.npz")
     a = torch.from_numpy(g[f"{mode}_a"]).cuda(); pv = torch.from_numpy(g[f"{mode}_pv"]).cuda()
     pa = torch.from_numpy(g[f"{mode}_pa"]).cuda(); p = torch.from_numpy(g[f"{mode}_p"]).cuda()
     rew, grad = pg_reward(a, pv, pa, p, mode=mode, normalise=True)
+    want_g = g[f"{mode}_grad"].reshape(grad.shape)
+    if mode == "sharpe_ratio":
+        # mean(ret) / std(ret) with std ≈ 3e-3 of values ≈ 1: fp32 rounding of the returns (6e-8) is amplified by 1 / std in the
+        # ratio and by 1 / std^2 in its gradient — the bounds below are that amplification, not slack in the kernel
+        np.testing.assert_allclose(rew.mean().item(), float(g[f"{mode}_r"]), rtol=2e-4)
+        np.testing.assert_allclose(grad.cpu().numpy(), want_g, rtol=5e-3, atol=2e-3 * np.abs(want_g).max())
+        return
     np.testing.assert_allclose(rew.mean().item(), float(g[f"{mode}_r"]), rtol=1e-5, atol=1e-7)
-    np.testing.assert_allclose(grad.cpu().numpy(), g[f"{mode}_grad"].reshape(grad.shape), rtol=2e-4, atol=2e-8)
+    np.testing.assert_allclose(grad.cpu().numpy(), want_g, rtol=2e-4, atol=2e-8)
 
 
 def test_pg_reward_autograd_function():
