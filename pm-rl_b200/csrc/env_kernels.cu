@@ -35,7 +35,7 @@ constexpr bool kDeferY = HASC && (NPL == 8 || NPL == 16);
 template <int NPL, bool HASC, bool PIPE>
 constexpr int kStepMinBlocks = PIPE ? 2 : NPL <= 2 ? 4 : NPL == 4 ? 3 : kDeferY<NPL, HASC> ? 3 : NPL == 32 ? 1 : 2;
 
-template <int NPL, bool HASC, int VEC, bool PIPE, bool TAIL>
+template <int NPL, bool HASC, int VEC, bool PIPE, bool TAIL, bool NOSINKS = false>
 __global__ void __launch_bounds__(kStepThreads, kStepMinBlocks<NPL, HASC, PIPE>) k_env_step(const StepParams p) {
     __shared__ double s_stats[kStepWarps * PMRL_STATS_LEN];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepMinBlocks<NPL, HASC, PIPE>)
         for (; e < p.E; e += nw) {
             if (e + 2 * nw < p.E) env_load_scalars(p, e + 2 * nw, s2);
             if (e + nw < p.E) env_load_vectors<NPL, HASC, VEC, TAIL>(p, e + nw, lane, s1, v1);
-            env_compute_store<NPL, HASC, VEC, TAIL>(p, e, lane, s0, v0, so, ws);
+            env_compute_rows<NPL, HASC, VEC, TAIL, true, true, false, NoHook, false, NOSINKS>(p, e, lane, s0, v0.a, v0.y, v0.wl, so, ws);
             s0 = s1; s1 = s2; v0 = v1;
         }
     } else {
@@ -376,7 +376,15 @@ static int launch_step_s(const StepParams& p, int npl, int vec, cudaStream_t s) 
         constexpr int NPL = decltype(N)::value, VEC = decltype(V)::value;
         // TAIL: every group of 32·VEC asset slots but the last is full → only the last group carries validity guards
         const bool tail = env_tail_ok<NPL, VEC>(p.A);
+        // (the pipelined form — large batches of narrow envs — has a variant without the per-env null tests of the PmrlStepIO sinks)
+        const bool nosinks = !p.action_sink && !p.weight_sink && !p.value_sink && !p.index_sink && !p.reward_host;
         auto go = [&](auto H, auto P, auto T) {
+            if constexpr (decltype(P)::value) {
+                if (nosinks) {
+                    k_env_step<NPL, decltype(H)::value, VEC, true, decltype(T)::value, true><<<grid, kStepThreads, 0, s>>>(p);
+                    return pmrl_check_launch("k_env_step");
+                }
+            }
             k_env_step<NPL, decltype(H)::value, VEC, decltype(P)::value, decltype(T)::value><<<grid, kStepThreads, 0, s>>>(p);
             return pmrl_check_launch("k_env_step");
         };
