@@ -41,6 +41,9 @@ WORKLOADS = {
     "c5_obs": (32768, 500, 50, 5, 0.0025, True, "wide universe with obs: 32,768 envs x 500 assets x window 50, commission 0.0025, obs materialised"),
     "c4_state": (131072, 100, 50, 5, 0.0, False, "config 4 shard, state-only step (no obs)"),
     "c4_f9": (131072, 100, 50, 9, 0.0, True, "config 4 shard with the indicator set appended: F = 9 (OHLC + ema + bbands + weight channel)"),
+    "c4_f13": (65536, 100, 50, 13, 0.0, True, "wider indicator set: F = 13 (OHLC + 8 indicator outputs + weight channel), 65,536 envs/GPU"),
+    "c4_f17": (65536, 100, 50, 17, 0.0, True, "wider indicator set: F = 17 (OHLC + 12 indicator outputs + weight channel), 65,536 envs/GPU"),
+    "c4_f7": (65536, 100, 50, 7, 0.0, True, "F = 7 ((F - 1) % 4 != 0, e.g. OHLC + two indicator outputs): fused kernel on the channel-padded table, 65,536 envs/GPU"),
 }
 EPISODE_LEN = 1000
 TABLE_ROWS = 4096
@@ -388,7 +391,7 @@ def config_entry(ctx, name, steps, warmup, mode="step", K=0, e2e=True, flushed=F
     """One entry of `configs`: the named BASELINE workload (its total env count divided over the ranks), timed on its own."""
     torch = ctx.torch
     E_total, A, W, F, commission, obs, desc = WORKLOADS[name]
-    per_gpu = name in ("c4_shard", "c4_state", "c5_obs", "c4_f9")
+    per_gpu = name in ("c4_shard", "c4_state", "c5_obs", "c4_f9", "c4_f13", "c4_f17", "c4_f7")
     E = E_total if per_gpu else E_total // ctx.world
     env = make_env(ctx, E, A, W, F, commission, ctx.rank * E)
     pool = action_pool(ctx, E, A)
@@ -701,6 +704,7 @@ def main():
         add("c3_collect", config3_entry, ctx, ks, kw)
         add("c4_state", config_entry, ctx, "c4_state", ks, kw)
         add("c4_f9", config_entry, ctx, "c4_f9", ks, kw, e2e=False)
+        add("c4_f7", config_entry, ctx, "c4_f7", ks, kw, e2e=False)
         add("c4_collect", collect_on_policy_entry, ctx, ks, kw, ms / args.steps)
         add("c5", config_entry, ctx, "c5", ks, kw)
         add("c5_burst15", config_entry, ctx, "c5", 15, 15, mode="burst", K=15)

@@ -52,7 +52,8 @@
 extern "C" {
 #endif
 
-#define PMRL_ABI_VERSION 4   /* 3: PmrlEnvState.ticket, PmrlStepIO + pmrl_env_step_io, pmrl_env_step_burst, pmrl_rollout_gather_index;
+#define PMRL_ABI_VERSION 5   /* 5: PmrlTables.feat_am4 (channel-padded feature table: fused kernel for any F <= 17);
+                                3: PmrlEnvState.ticket, PmrlStepIO + pmrl_env_step_io, pmrl_env_step_burst, pmrl_rollout_gather_index;
                                 4: PmrlStepIO.actions_ready (action rows streamed in under the kernel) */
 
 /* error codes (negative) */
@@ -92,6 +93,10 @@ typedef struct PmrlTables {
     const float* y_tm;         /* [T, A] price relatives y[t] = close[t] / close[t-1] (row 0 = 1) built by
                                   pmrl_price_relatives from the time-major close plane, or NULL when y is supplied externally */
     const float* feat_am;      /* [A, T, F-1] or NULL when obs_mode != PMRL_OBS_FULL */
+    const float* feat_am4;     /* optional: the same table with every (asset, row) padded to a multiple of four channels,
+                                  [A, T, 4*ceil((F-1)/4)], 16-byte aligned (pad values are never copied to obs).  With it the
+                                  fused step+obs kernel covers every F in [2, 17]; without it only (F-1) % 4 == 0, other widths
+                                  take the state-only step followed by the obs tile kernel.  NULL → not provided. */
 } PmrlTables;
 
 typedef struct PmrlEnvState {

@@ -24,7 +24,7 @@ class PmrlEnvCfg(C.Structure):
 
 
 class PmrlTables(C.Structure):
-    _fields_ = [("y_tm", c_void_p), ("feat_am", c_void_p)]
+    _fields_ = [("y_tm", c_void_p), ("feat_am", c_void_p), ("feat_am4", c_void_p)]
 
 
 class PmrlEnvState(C.Structure):
@@ -106,7 +106,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here means header and library diverged
         fn.restype = res
         fn.argtypes = args
-    if lib.pmrl_abi_version() != 4:
+    if lib.pmrl_abi_version() != 5:
         raise PmrlError("libpmrl_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -301,7 +301,7 @@ static int fill_params(const PmrlEnvCfg* cfg, const PmrlTables* tbl, const PmrlE
     const double c = (double)cfg->commission;
     p.mu0 = (float)(1.0 - 2.0 * c + c * c);
     p.c2 = (float)(2.0 * c - c * c);
-    if (tbl) { p.y_tm = tbl->y_tm; p.feat_am = tbl->feat_am; }
+    if (tbl) { p.y_tm = tbl->y_tm; p.feat_am = tbl->feat_am; p.feat_am4 = tbl->feat_am4; }
     p.value = st->value; p.hist = st->hist; p.idx = st->idx; p.is_full = st->is_full; p.t = st->t;
     p.t0 = st->t0; p.sharpe = st->sharpe; p.ep_return = st->ep_return;
     p.ticket = st->ticket;

@@ -32,11 +32,12 @@ constexpr int kRtGroupNarrow = 2 * kRtWarps;       // A <= 64: two envs per warp
 
 struct RtEnv { int row0, shift, fresh_slot, pad; };
 
-// Tile geometry for C4 = (F - 1) / 4 float4 chunks per (asset, table row): F = 5, 9, 13, 17 (OHLC, OHLC + indicator outputs).
+// Tile geometry for C4 = ceil((F - 1) / 4) float4 chunks per (asset, table row): F <= 5, 9, 13, 17 (OHLC, OHLC + indicator
+// outputs).  When (F - 1) % 4 != 0 the chunks come from the channel-padded table PmrlTables.feat_am4 and the last chunk of a
+// row stores only its (F - 1) - 4 (C4 - 1) real channels.
 // A warp owns RPW asset rows of a tile and stages ≤ 8 float4 per thread one tile ahead, so wider rows mean lower tiles:
 // 32 rows at F = 5 (32 KB at W = 50), 16 at F = 9 (28.8 KB), 8 at F = 13 / 17.
 template <int C4> struct RtGeom {
-    static constexpr int F = 4 * C4 + 1;
     static constexpr int RPW = C4 == 1 ? 4 : C4 == 2 ? 2 : 1;      // asset rows per warp and tile
     static constexpr int TR = 8 * RPW;                             // asset rows per tile
     static constexpr int NSUB = 32 / TR;                           // lane groups sharing the weight channel of a tile row
@@ -47,11 +48,15 @@ template <int C4, int WT> struct RtFeat {
     float4 fv[RtGeom<C4>::RPW][MW];
 };
 
-template <int NPL, bool HASC, int VEC, int WT, int C4>
+// PAD = false: F = 4 C4 + 1 is a compile-time constant (every tile offset folds); PAD = true: F = p.F at run time, chunks from
+// the channel-padded table (measured: a run-time F in the headline instantiation costs 8 %, hence the split).
+template <int NPL, bool HASC, int VEC, int WT, int C4, bool PAD = false>
 __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepParams p) {
     using Geo = RtGeom<C4>;
     using Feat = RtFeat<C4, WT>;
-    constexpr int F = Geo::F, RPW = Geo::RPW, TR = Geo::TR, NSUB = Geo::NSUB, JMAX = Geo::JMAX, MW = Feat::MW;
+    constexpr int RPW = Geo::RPW, TR = Geo::TR, NSUB = Geo::NSUB, JMAX = Geo::JMAX, MW = Feat::MW;
+    const int F = PAD ? p.F : 4 * C4 + 1;                            // PAD: 4 (C4 - 1) + 1 < F < 4 C4 + 1
+    const int cv = PAD ? F - 1 - 4 * (C4 - 1) : 4;                   // real channels in the last chunk of a row
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_stats[kRtWarps * PMRL_STATS_LEN];
     __shared__ RtEnv s_env[kRtGroupNarrow];
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
     const int wbase = (rl * W + warp + 8 * sub) * F + (F - 1);
     const int n8 = max(0, (W - warp + 7) >> 3);                      // window slots warp, warp + 8, … below W
     const int nj = n8 > sub ? (n8 - sub + NSUB - 1) / NSUB : 0;
-    const float4* __restrict__ tbl = reinterpret_cast<const float4*>(p.feat_am) + lane * C4;
+    const float4* __restrict__ tbl = reinterpret_cast<const float4*>(PAD ? p.feat_am4 : p.feat_am) + lane * C4;
 
     int buf = 0;
     int ebase = 0;                                                   // envs streamed by this CTA so far (ring buffer / phase index)
@@ -189,7 +194,13 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
                         if (w < W) {
                             float* d = drow + w * F + 4 * (m % C4);
                             const float4 v = fr.fv[i][m];
-                            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                            if (!PAD || m % C4 < C4 - 1) { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+                            else {                                    // last chunk of the row: cv real channels, the rest is padding
+                                d[0] = v.x;
+                                if (cv > 1) d[1] = v.y;
+                                if (cv > 2) d[2] = v.z;
+                                if (cv > 3) d[3] = v.w;
+                            }
                         }
                     }
                 }
@@ -262,25 +273,25 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
 
 using namespace pmrl;
 
-template <int NPL, bool HASC, int VEC, int WT, int C4>
+template <int NPL, bool HASC, int VEC, int WT, int C4, bool PAD>
 static int launch_rt_t(StepParams& p, size_t smem, int grid, cudaStream_t s) {
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs_rt<NPL, HASC, VEC, WT, C4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_env_step_obs_rt<NPL, HASC, VEC, WT, C4, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return pmrl_fail((int)e, "cudaFuncSetAttribute(k_env_step_obs_rt) failed");
         attr_done[dev] = true;
     }
-    k_env_step_obs_rt<NPL, HASC, VEC, WT, C4><<<grid, kRtThreads, smem, s>>>(p);
+    k_env_step_obs_rt<NPL, HASC, VEC, WT, C4, PAD><<<grid, kRtThreads, smem, s>>>(p);
     return pmrl_check_launch("k_env_step_obs_rt");
 }
 
-template <int NPL, int VEC, int C4>
+template <int NPL, int VEC, int C4, bool PAD>
 static int launch_rt_w(StepParams& p, size_t smem, int grid, cudaStream_t s) {
     const bool hasc = p.commission > 0.0f;
-    if (p.W == 50) return hasc ? launch_rt_t<NPL, true, VEC, 50, C4>(p, smem, grid, s) : launch_rt_t<NPL, false, VEC, 50, C4>(p, smem, grid, s);
-    return hasc ? launch_rt_t<NPL, true, VEC, 0, C4>(p, smem, grid, s) : launch_rt_t<NPL, false, VEC, 0, C4>(p, smem, grid, s);
+    if (p.W == 50) return hasc ? launch_rt_t<NPL, true, VEC, 50, C4, PAD>(p, smem, grid, s) : launch_rt_t<NPL, false, VEC, 50, C4, PAD>(p, smem, grid, s);
+    return hasc ? launch_rt_t<NPL, true, VEC, 0, C4, PAD>(p, smem, grid, s) : launch_rt_t<NPL, false, VEC, 0, C4, PAD>(p, smem, grid, s);
 }
 
 // Envs per group for a batch of E envs on `slots` persistent CTAs.  A CTA's time is (rounds it runs) x (envs per group +
@@ -301,9 +312,12 @@ static int pick_group(int E, int slots, int gmax) {
 }
 
 int pmrl_launch_step_obs_rt(StepParams& p, int npl, int vec, int group, int ctas_per_sm, cudaStream_t s) {
-    // F = 5, 9, 13, 17: four feature channels per float4 chunk of the asset-major table (OHLC, OHLC + indicator outputs)
-    if (p.F < 5 || p.F > 17 || (p.F - 1) % 4 != 0 || ((uintptr_t)p.feat_am) % 16 != 0) return -100;
-    const int c4 = (p.F - 1) / 4;
+    // four feature channels per float4 chunk of the asset-major table: F = 5, 9, 13, 17 read feat_am directly, every other
+    // F in [2, 17] needs the channel-padded copy feat_am4
+    if (p.F < 2 || p.F > 17) return -100;
+    const float* tbl = (p.F - 1) % 4 == 0 ? p.feat_am : p.feat_am4;
+    if (!tbl || ((uintptr_t)tbl) % 16 != 0) return -100;
+    const int c4 = (p.F + 2) / 4;                                     // ceil((F - 1) / 4)
     if (p.W > 64 || npl > 4 || p.A < 32) return -100;                 // A >= 32: a tile spans at most two envs
     if (((size_t)p.W * p.A) % 4 != 0 || ((uintptr_t)p.hist) % 16 != 0) return -100;   // every env's ring 16-byte aligned
     if ((size_t)p.A * p.T * c4 >= (1u << 31) || p.A >= 65536) return -100;
@@ -326,12 +340,19 @@ int pmrl_launch_step_obs_rt(StepParams& p, int npl, int vec, int group, int ctas
     const size_t smem = fixed + (size_t)p.ring_bufs * ring_bytes;
     const int n_groups = (p.E + G - 1) / G;
     const int grid = n_groups < slots ? n_groups : slots;
-#define RT_CASE(N, V, C) if (npl == N && vec == V && c4 == C) return launch_rt_w<N, V, C>(p, smem, grid, s)
+    const bool pad = (p.F - 1) % 4 != 0;
+#define RT_CASE(N, V, C) if (npl == N && vec == V && c4 == C && !pad) return launch_rt_w<N, V, C, false>(p, smem, grid, s)
+#define RT_PAD(N, V, C) if (npl == N && vec == V && c4 == C && pad) return launch_rt_w<N, V, C, true>(p, smem, grid, s)
     RT_CASE(1, 1, 1); RT_CASE(2, 1, 1); RT_CASE(2, 2, 1); RT_CASE(4, 1, 1); RT_CASE(4, 2, 1); RT_CASE(4, 4, 1);
-    // wider feature sets: the even / 16-byte asset maps only (odd asset counts take the two-kernel path)
+    // wider feature sets and padded tables: the even / 16-byte asset maps only (odd asset counts take the two-kernel path)
     RT_CASE(2, 2, 2); RT_CASE(4, 2, 2); RT_CASE(4, 4, 2);
     RT_CASE(2, 2, 3); RT_CASE(4, 2, 3); RT_CASE(4, 4, 3);
     RT_CASE(2, 2, 4); RT_CASE(4, 2, 4); RT_CASE(4, 4, 4);
+    RT_PAD(2, 2, 1); RT_PAD(4, 2, 1); RT_PAD(4, 4, 1);
+    RT_PAD(2, 2, 2); RT_PAD(4, 2, 2); RT_PAD(4, 4, 2);
+    RT_PAD(2, 2, 3); RT_PAD(4, 2, 3); RT_PAD(4, 4, 3);
+    RT_PAD(2, 2, 4); RT_PAD(4, 2, 4); RT_PAD(4, 4, 4);
 #undef RT_CASE
+#undef RT_PAD
     return -100;
 }

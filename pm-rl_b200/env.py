@@ -134,7 +134,14 @@ class BatchedTradingEnv:
             self.y_tm = torch.empty_like(self.close_tm)
             _lib.check(self.lib.pmrl_price_relatives(self.close_tm.data_ptr(), self.T, A, self.y_tm.data_ptr(),
                                                      _lib.current_stream()), "pmrl_price_relatives")
-        self._c_tbl = _lib.PmrlTables(_lib.ptr(self.y_tm), _lib.ptr(self.feat_am))
+        # channel-padded copy of the feature table ([A, T, 4*ceil((F-1)/4)]) for the fused step+obs kernel when F - 1 is not a
+        # multiple of four (e.g. OHLC + ema: F = 6, OHLC + bbands: F = 8); the pad channels are never copied to obs
+        self.feat_am4 = None
+        if self.feat_am is not None and (F - 1) % 4 != 0 and F <= 17:
+            c4 = (F + 2) // 4
+            self.feat_am4 = torch.zeros(A, self.T, 4 * c4, dtype=torch.float32, device=dev)
+            self.feat_am4[:, :, :F - 1] = self.feat_am
+        self._c_tbl = _lib.PmrlTables(_lib.ptr(self.y_tm), _lib.ptr(self.feat_am), _lib.ptr(self.feat_am4))
         self._c_st = _lib.PmrlEnvState(_lib.ptr(self.value), _lib.ptr(self.hist), _lib.ptr(self.idx),
                                        _lib.ptr(self.is_full), _lib.ptr(self.t), _lib.ptr(self.t0),
                                        _lib.ptr(self.sharpe), _lib.ptr(self.ep_return), _lib.ptr(self._ticket))

@@ -31,7 +31,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} is declared in include/pmrl_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared_symbols(), "ctypes signature table and header diverged"
-    assert _lib.load().pmrl_abi_version() == 4
+    assert _lib.load().pmrl_abi_version() == 5
 
 
 def test_ctypes_structs_match_the_c_layout():
