@@ -115,7 +115,9 @@ VARIANTS = [(1, 0, 1, 1), (1, 3, 1, 1), (1, 5, 1, 1), (1, 7, 1, 1), (1, 12, 1, 1
                                      (33, 9, 6, 48), (130, 16, 2, 40), (1, 4, 5, 9), (3, 300, 5, 5),
                                      # wider feature sets (OHLC + indicator outputs): fused kernel at F = 9 / 13 / 17, tile kernels else
                                      (100, 50, 9, 45), (50, 50, 9, 37), (64, 24, 13, 37), (36, 20, 17, 30), (100, 50, 7, 20),
-                                     (40, 16, 12, 33), (34, 10, 3, 41)])
+                                     (40, 16, 12, 33), (34, 10, 3, 41),
+                                     # every chunk count of the channel-padded fused path (PmrlTables.feat_am4)
+                                     (64, 12, 2, 30), (36, 20, 6, 30), (100, 24, 8, 20), (52, 10, 10, 25), (44, 9, 14, 21), (32, 8, 16, 19)])
 def test_table_driven_step_and_obs_vs_oracle(A, W, F, E, variant, tuning):
     """Batched, table-driven: window gather, y from the close plane, ring wrap, done and auto-reset."""
     fused, group, rt, fast = variant
