@@ -5,7 +5,7 @@ out=${1:-profiles/r02_sass_k_env_step_obs_rt_and_staged.txt}
 echo "# SASS evidence (cuobjdump -sass pm-rl_b200/libpmrl_b200.so, sm_100a cubins only) — TMA bulk copies (UBLKCP), mbarrier waits (SYNCS),"
 echo "# L2 prefetch (CCTL.E.PF2), no-L1-allocate 16-byte loads (LDG.E.NA.128), packed fp32 (FADD2/FMUL2/FFMA2), 3-input min/max (FMNMX3)."
 echo "# Regenerate: tools/sass_excerpt.sh"
-for fn in '_ZN4pmrl17k_env_step_obs_rtILi4ELb0ELi4ELi50ELi1EEEvNS_10StepParamsE' '_ZN4pmrl17k_env_step_obs_rtILi4ELb0ELi4ELi50ELi2EEEvNS_10StepParamsE' '_ZN4pmrl17k_env_step_obs_rtILi2ELb0ELi2ELi50ELi1EEEvNS_10StepParamsE' '_ZN4pmrl17k_env_step_stagedILi16ELb1ELb1ELi8ELi2ELb1EEEvNS_10StepParamsE'; do
+for fn in '_ZN4pmrl17k_env_step_obs_rtILi4ELb0ELi4ELi50ELi1ELb0EEEvNS_10StepParamsE' '_ZN4pmrl17k_env_step_obs_rtILi4ELb0ELi4ELi50ELi2ELb0EEEvNS_10StepParamsE' '_ZN4pmrl17k_env_step_obs_rtILi2ELb0ELi2ELi50ELi1ELb0EEEvNS_10StepParamsE' '_ZN4pmrl17k_env_step_stagedILi16ELb1ELb1ELi8ELi2ELb1EEEvNS_10StepParamsE'; do
   echo; echo "## $(echo $fn | c++filt)"
   cuobjdump -sass -fun "$fn" pm-rl_b200/libpmrl_b200.so > /tmp/k.sass 2>/dev/null
   echo "arch: $(grep -m1 'arch =' /tmp/k.sass)"
