@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kStgWarps * 32, MINB) k_env_step_staged(const 
     auto issue = [&](int e, const EnvScalars& s, int st) {
         if (env_needs_reset(p, s)) return;                           // the auto-reset call reads nothing
         if (lane == 0) {
-            if (p.act_ready) { env_wait_actions_lane(p, e); asm volatile("fence.proxy.async;" ::: "memory"); }
+            if (!NOSINKS && p.act_ready) { env_wait_actions_lane(p, e); asm volatile("fence.proxy.async;" ::: "memory"); }
             fence_proxy_async_smem();
             float* dst = my_rows + (size_t)st * R * A;
             uint64_t* bar = &s_bar[warp][st];
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kStgWarps * 32, MINB) k_env_step_staged1(const
     if (e < p.E) {
         env_load_scalars(p, e, s0);
         if (!env_needs_reset(p, s0) && lane == 0) {
-            if (p.act_ready) { env_wait_actions_lane(p, e); asm volatile("fence.proxy.async;" ::: "memory"); }
+            if (!NOSINKS && p.act_ready) { env_wait_actions_lane(p, e); asm volatile("fence.proxy.async;" ::: "memory"); }
             mbar_arrive_expect_tx(bar_a, (WLR ? 2u : 1u) * row_bytes);
             bulk_load_g2s(my_rows, p.actions + (size_t)e * A, row_bytes, bar_a, kPolicyEvictFirst);
             if (WLR) bulk_load_g2s(my_rows + 2 * A, wl_row(e, s0), row_bytes, bar_a, kPolicyEvictFirst);
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kStgWarps * 32, MINB) k_env_step_staged1(const
         }
         __syncwarp();                                                // every lane holds its part of the action row
         if (next_live && lane == 0) {
-            if (p.act_ready) { env_wait_actions_lane(p, e + nw); asm volatile("fence.proxy.async;" ::: "memory"); }
+            if (!NOSINKS && p.act_ready) { env_wait_actions_lane(p, e + nw); asm volatile("fence.proxy.async;" ::: "memory"); }
             fence_proxy_async_smem();
             mbar_arrive_expect_tx(bar_a, (WLR ? 2u : 1u) * row_bytes);
             bulk_load_g2s(my_rows, p.actions + (size_t)(e + nw) * A, row_bytes, bar_a, kPolicyEvictFirst);
@@ -213,7 +213,8 @@ static int launch_staged_t(const StepParams& p, cudaStream_t s) {
     int per_sm = (int)(((size_t)226 * 1024) / (smem + 2048));
     if (per_sm > MINB) per_sm = MINB;
     void (*kern)(const StepParams);
-    const bool nosinks = !p.action_sink && !p.weight_sink && !p.value_sink && !p.index_sink && !p.reward_host;
+    // (NOSINKS instantiations also drop the wait for streamed-in action rows: the two rarely-used features share one variant)
+    const bool nosinks = !p.action_sink && !p.weight_sink && !p.value_sink && !p.index_sink && !p.reward_host && !p.act_ready;
     if constexpr (STAGES == 2) kern = nosinks ? k_env_step_staged<NPL, HASC, TAIL, WARPS, MINB, true> : k_env_step_staged<NPL, HASC, TAIL, WARPS, MINB, false>;
     else kern = nosinks ? k_env_step_staged1<NPL, HASC, TAIL, WARPS, MINB, true, STAGES_ == 1> : k_env_step_staged1<NPL, HASC, TAIL, WARPS, MINB, false, STAGES_ == 1>;
     static bool attr_done[64][2] = {{false}};
