@@ -43,6 +43,8 @@ WORKLOADS = {
     "c4_f9": (131072, 100, 50, 9, 0.0, True, "config 4 shard with the indicator set appended: F = 9 (OHLC + ema + bbands + weight channel)"),
     "c4_f13": (65536, 100, 50, 13, 0.0, True, "wider indicator set: F = 13 (OHLC + 8 indicator outputs + weight channel), 65,536 envs/GPU"),
     "c4_f17": (65536, 100, 50, 17, 0.0, True, "wider indicator set: F = 17 (OHLC + 12 indicator outputs + weight channel), 65,536 envs/GPU"),
+    "c4_f6": (65536, 100, 50, 6, 0.0, True, "F = 6 (OHLC + ema + weight channel), 65,536 envs/GPU"),
+    "c4_f8": (65536, 100, 50, 8, 0.0, True, "F = 8 (OHLC + bbands + weight channel), 65,536 envs/GPU"),
     "c4_f7": (65536, 100, 50, 7, 0.0, True, "F = 7 ((F - 1) % 4 != 0, e.g. OHLC + two indicator outputs): fused kernel on the channel-padded table, 65,536 envs/GPU"),
 }
 EPISODE_LEN = 1000
@@ -391,7 +393,7 @@ def config_entry(ctx, name, steps, warmup, mode="step", K=0, e2e=True, flushed=F
     """One entry of `configs`: the named BASELINE workload (its total env count divided over the ranks), timed on its own."""
     torch = ctx.torch
     E_total, A, W, F, commission, obs, desc = WORKLOADS[name]
-    per_gpu = name in ("c4_shard", "c4_state", "c5_obs", "c4_f9", "c4_f13", "c4_f17", "c4_f7")
+    per_gpu = name in ("c4_shard", "c4_state", "c5_obs", "c4_f9", "c4_f13", "c4_f17", "c4_f7", "c4_f6", "c4_f8")
     E = E_total if per_gpu else E_total // ctx.world
     env = make_env(ctx, E, A, W, F, commission, ctx.rank * E)
     pool = action_pool(ctx, E, A)

@@ -89,6 +89,15 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
     const int n8 = max(0, (W - warp + 7) >> 3);                      // window slots warp, warp + 8, … below W
     const int nj = n8 > sub ? (n8 - sub + NSUB - 1) / NSUB : 0;
     const float4* __restrict__ tbl = reinterpret_cast<const float4*>(PAD ? p.feat_am4 : p.feat_am) + lane * C4;
+    // Even F (PAD instantiations only): a row pitch of F floats puts the lanes-over-window-rows stores on 32 / gcd(F, 32) banks.
+    // With 2-way conflicts the chunk form still wins (F = 6 at 65,536 x 100: 2.13 ms = 0.66 against 3.12 ms dense), with 8-way
+    // it does not (F = 8: 3.78 ms = 0.48 against 3.16 ms = 0.57 dense), so F = 8 and 16 take the DENSE form: lane l owns floats l, l + 32, … of the asset row's W·F-float image, loads feature (w, c) = (n / F, n % F)
+    // as a scalar from the UNPADDED table (index n - w: consecutive lanes read consecutive floats but for one gap per
+    // window row) and stores it to offset n — consecutive banks, conflict-free for every F.  The weight slot c = F - 1 is
+    // skipped (the weight pass below fills it).
+    const bool dense = PAD && (F & 7) == 0;
+    const unsigned inv_f = PAD ? (65536u + (unsigned)F - 1u) / (unsigned)F : 0u;   // n / F = (n * inv_f) >> 16 for n < 64 * 17
+    constexpr int MD = 8 * C4;                                       // floats of a row image per lane (W <= 64, F <= 4 C4 + 1)
 
     int buf = 0;
     int ebase = 0;                                                   // envs streamed by this CTA so far (ring buffer / phase index)
@@ -174,6 +183,20 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
             for (int i = 0; i < RPW; ++i) {
                 if (!PARTIAL || warp + 8 * i < nr) {
                     const int ea = s_ea[r0 + warp + 8 * i];
+                    if constexpr (PAD) {
+                        if (dense) {
+                            const float* __restrict__ srcd = p.feat_am + (size_t)((ea & 0xffff) * T + s_env[ea >> 16].row0) * (F - 1);
+                            float* const dv = reinterpret_cast<float*>(&fr.fv[i][0]);
+                            const int nrow = W * F;
+#pragma unroll
+                            for (int m = 0; m < MD; ++m) {
+                                const int n = lane + 32 * m;
+                                const int w = (int)(((unsigned)n * inv_f) >> 16);
+                                if (n < nrow && n - w * F != F - 1) dv[m] = ld_keep(srcd + (n - w), kPolicyEvictLast);
+                            }
+                            continue;
+                        }
+                    }
                     const float4* __restrict__ src = tbl + (size_t)((ea & 0xffff) * T + s_env[ea >> 16].row0) * C4;
 #pragma unroll
                     for (int m = 0; m < MW; ++m)                      // m = (m / C4)-th window row of this lane, chunk m % C4
@@ -188,6 +211,19 @@ __global__ void __launch_bounds__(kRtThreads, 2) k_env_step_obs_rt(const StepPar
             for (int i = 0; i < RPW; ++i) {
                 if (!PARTIAL || warp + 8 * i < nr) {
                     float* drow = tile + (warp + 8 * i) * W * F;
+                    if constexpr (PAD) {
+                        if (dense) {
+                            const float* const dv = reinterpret_cast<const float*>(&fr.fv[i][0]);
+                            const int nrow = W * F;
+#pragma unroll
+                            for (int m = 0; m < MD; ++m) {
+                                const int n = lane + 32 * m;
+                                const int w = (int)(((unsigned)n * inv_f) >> 16);
+                                if (n < nrow && n - w * F != F - 1) drow[n] = dv[m];
+                            }
+                            continue;
+                        }
+                    }
 #pragma unroll
                     for (int m = 0; m < MW; ++m) {
                         const int w = lane + 32 * (m / C4);
@@ -315,8 +351,8 @@ int pmrl_launch_step_obs_rt(StepParams& p, int npl, int vec, int group, int ctas
     // four feature channels per float4 chunk of the asset-major table: F = 5, 9, 13, 17 read feat_am directly, every other
     // F in [2, 17] needs the channel-padded copy feat_am4
     if (p.F < 2 || p.F > 17) return -100;
-    const float* tbl = (p.F - 1) % 4 == 0 ? p.feat_am : p.feat_am4;
-    if (!tbl || ((uintptr_t)tbl) % 16 != 0) return -100;
+    const float* tbl = (p.F - 1) % 4 == 0 || p.F % 8 == 0 ? p.feat_am : p.feat_am4;   // F = 8, 16: dense scalar loads from feat_am
+    if (!tbl || (p.F % 8 != 0 && ((uintptr_t)tbl) % 16 != 0)) return -100;
     const int c4 = (p.F + 2) / 4;                                     // ceil((F - 1) / 4)
     if (p.W > 64 || npl > 4 || p.A < 32) return -100;                 // A >= 32: a tile spans at most two envs
     if (((size_t)p.W * p.A) % 4 != 0 || ((uintptr_t)p.hist) % 16 != 0) return -100;   // every env's ring 16-byte aligned
